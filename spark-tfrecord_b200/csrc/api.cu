@@ -1,0 +1,759 @@
+// api.cu -- the C ABI of libtfrgpu.so (include/tfrgpu.h) and the host-side runtime above the kernels:
+// schema lowering, per-task decoder/encoder handles (device + stream + reusable buffers), batch
+// ownership, host copies and Arrow C Data Interface export.  No torch types, no CPU fallback: every
+// compute path below launches the sm_100a kernels of frame.cuh / decode.cuh / scan.cuh / encode.cuh.
+#include <cuda_runtime.h>
+#include <algorithm>
+#include <atomic>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+#include "decode.cuh"
+#include "encode.cuh"
+#include "frame.cuh"
+#include "host_util.h"
+#include "scan.cuh"
+
+// ---------------------------------------------------------------------------------------------
+// errors
+// ---------------------------------------------------------------------------------------------
+static thread_local std::string g_last_error;
+static int32_t fail(int32_t code, const std::string& msg) { g_last_error = msg; return code; }
+#define CUDA_TRY(expr)                                                                             \
+  do {                                                                                             \
+    cudaError_t _e = (expr);                                                                       \
+    if (_e != cudaSuccess) return fail(TFR_E_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e)); \
+  } while (0)
+
+int32_t DevBuf::ensure(size_t bytes) {
+  cudaError_t e = ensure_raw(bytes);
+  if (e != cudaSuccess) return fail(e == cudaErrorMemoryAllocation ? TFR_E_OOM : TFR_E_CUDA, std::string("device allocation failed: ") + cudaGetErrorString(e));
+  return TFR_OK;
+}
+#define TRY(expr) do { int32_t _rc = (expr); if (_rc) return _rc; } while (0)
+
+extern "C" int32_t tfr_abi_version(void) { return TFR_ABI_VERSION; }
+extern "C" const char* tfr_last_error(void) { return g_last_error.c_str(); }
+extern "C" const char* tfr_status_string(int32_t s) {
+  switch (s) {
+    case TFR_OK: return "ok";
+    case TFR_E_INVALID_ARG: return "invalid argument";
+    case TFR_E_UNSUPPORTED_TYPE: return "unsupported data type";
+    case TFR_E_BAD_RECORD_TYPE: return "unsupported recordType: recordType can be ByteArray, Example or SequenceExample";
+    case TFR_E_CUDA: return "CUDA error / no usable device";
+    case TFR_E_OOM: return "out of memory";
+    case TFR_E_BATCH_TOO_LARGE: return "batch too large (2 GiB of framed bytes / int32 Arrow offsets)";
+    case TFR_E_CRC_LENGTH: return "Length header crc32 checking failed";
+    case TFR_E_CRC_DATA: return "Data crc32 checking failed";
+    case TFR_E_TRUNCATED: return "End of file reached before reading fully";
+    case TFR_E_RECORD_TOO_LARGE: return "Record size exceeds max value of int32";
+    case TFR_E_MALFORMED_PROTO: return "Protocol message was malformed";
+    case TFR_E_KIND_MISMATCH: return "Feature must be of the list kind the column type requires";
+    case TFR_E_EMPTY_SCALAR: return "head of empty list";
+    case TFR_E_NULL_IN_NONNULL: return "field does not allow null values";
+    case TFR_E_BAD_NESTING: return "Cannot convert Feature/FeatureList to this array nesting";
+    default: return "unknown status";
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// per-device context: CRC tables
+// ---------------------------------------------------------------------------------------------
+struct DeviceCtx {
+  std::once_flag once;
+  CrcTables* d_tabs = nullptr;
+  cudaError_t err = cudaSuccess;
+  int sm_count = 148;
+};
+static DeviceCtx g_ctx[64];
+
+static void build_crc_tables(CrcTables& t) {
+  const uint32_t POLY = 0x82F63B78u;
+  for (uint32_t i = 0; i < 256; ++i) {
+    uint32_t c = i;
+    for (int k = 0; k < 8; ++k) c = (c >> 1) ^ (POLY & (0u - (c & 1u)));
+    t.t0[i] = c;
+  }
+  auto mulmod = [&](uint32_t a, uint32_t b) {
+    uint32_t p = 0;
+    for (int i = 31; i >= 0; --i) {
+      if ((a >> i) & 1u) p ^= b;
+      b = (b >> 1) ^ (POLY & (0u - (b & 1u)));
+    }
+    return p;
+  };
+  auto xpow_bytes = [&](uint32_t nbytes) {     // x^(8*nbytes) mod P
+    uint32_t x8 = 0x80000000u;
+    for (int i = 0; i < 8; ++i) x8 = (x8 >> 1) ^ (POLY & (0u - (x8 & 1u)));
+    uint32_t r = 0x80000000u, base = x8;
+    while (nbytes) { if (nbytes & 1) r = mulmod(r, base); base = mulmod(base, base); nbytes >>= 1; }
+    return r;
+  };
+  uint32_t x128 = xpow_bytes(128);
+  for (int s = 0; s < 4; ++s)
+    for (uint32_t b = 0; b < 256; ++b) t.k128[s][b] = mulmod(x128, b << (8 * s));
+  for (uint32_t k = 0; k < 40; ++k) t.xw[k] = xpow_bytes(4 * k);
+}
+
+static int32_t get_ctx(int device, DeviceCtx** out) {
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) return fail(TFR_E_CUDA, std::string("no CUDA device: ") + cudaGetErrorString(e));
+  if (device < 0 || device >= ndev || device >= 64) return fail(TFR_E_INVALID_ARG, "bad device index");
+  DeviceCtx& c = g_ctx[device];
+  std::call_once(c.once, [&] {
+    c.err = cudaSetDevice(device);
+    if (c.err != cudaSuccess) return;
+    cudaDeviceProp prop;
+    c.err = cudaGetDeviceProperties(&prop, device);
+    if (c.err != cudaSuccess) return;
+    c.sm_count = prop.multiProcessorCount;
+    CrcTables* h = new CrcTables;
+    build_crc_tables(*h);
+    c.err = cudaMalloc(&c.d_tabs, sizeof(CrcTables));
+    if (c.err == cudaSuccess) c.err = cudaMemcpy(c.d_tabs, h, sizeof(CrcTables), cudaMemcpyHostToDevice);
+    delete h;
+  });
+  if (c.err != cudaSuccess) return fail(TFR_E_CUDA, std::string("device init: ") + cudaGetErrorString(c.err));
+  *out = &c;
+  return TFR_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// schema
+// ---------------------------------------------------------------------------------------------
+struct tfr_schema {
+  int32_t record_type = 0;
+  std::vector<DevField> fields;      // device layout, filled on the host
+  std::vector<uint8_t> names;
+  std::vector<int32_t> ht;
+  std::vector<int32_t> var_field;    // var slot -> field
+  std::vector<int32_t> fix_field;    // fix slot -> field
+  int32_t n_fix = 0, n_var = 0, n_cnt = 0;
+};
+
+static uint32_t fnv1a(const uint8_t* p, uint32_t n) { uint32_t h = 2166136261u; for (uint32_t i = 0; i < n; ++i) h = (h ^ p[i]) * 16777619u; return h; }
+
+extern "C" int32_t tfr_schema_create(const tfr_field* fields, int32_t n_fields, int32_t record_type, tfr_schema** out) {
+  if (!out || n_fields < 0 || (n_fields > 0 && !fields)) return fail(TFR_E_INVALID_ARG, "null argument");
+  if (record_type < TFR_RT_EXAMPLE || record_type > TFR_RT_BYTE_ARRAY)
+    return fail(TFR_E_BAD_RECORD_TYPE, "Unsupported recordType: recordType can be ByteArray, Example or SequenceExample");
+  if (n_fields > 4096) return fail(TFR_E_INVALID_ARG, "more than 4096 fields");
+  auto* s = new tfr_schema;
+  s->record_type = record_type;
+  if (record_type == TFR_RT_BYTE_ARRAY) {
+    // the single binary column of TensorFlowInferSchema.getSchemaForByteArray (M/TensorFlowInferSchema.scala:60-64);
+    // the caller's field list is ignored like deserializeByteArray ignores the schema (:17-19)
+    DevField d{};
+    d.name_off = 0; d.name_len = 9; s->names.assign((const uint8_t*)"byteArray", (const uint8_t*)"byteArray" + 9);
+    d.hash = fnv1a(s->names.data(), 9);
+    d.elem_type = TFR_T_BINARY; d.depth = 0; d.nullable = 1; d.kind = K_BYTES; d.n_levels = 1; d.dup_next = -1;
+    d.fix_slot = -1; d.var_slot = 0; d.cnt_slot = 0; d.width = 1;
+    s->fields.push_back(d);
+    s->var_field.push_back(0);
+    s->n_var = 1; s->n_cnt = 1;
+    s->ht.assign(2, -1);
+    s->ht[d.hash & 1] = 0;
+    *out = s;
+    return TFR_OK;
+  }
+  for (int32_t i = 0; i < n_fields; ++i) {
+    const tfr_field& f = fields[i];
+    if (f.name_len < 0 || (f.name_len > 0 && !f.name)) { delete s; return fail(TFR_E_INVALID_ARG, "bad field name"); }
+    std::string nm(f.name ? f.name : "", (size_t)f.name_len);
+    // newFeatureWriter / newFeatureConverter: anything but these types throws (M/TFRecordDeserializer.scala:119-123,
+    // M/TFRecordSerializer.scala:147,151); ArrayType(NullType) falls into the same default branch
+    bool ok_type = f.elem_type >= TFR_T_NULL && f.elem_type <= TFR_T_BINARY && f.depth >= 0 && f.depth <= 2 &&
+                   !(f.elem_type == TFR_T_NULL && f.depth > 0);
+    if (!ok_type) { delete s; return fail(TFR_E_UNSUPPORTED_TYPE, "field '" + nm + "': data type is not supported"); }
+    DevField d{};
+    d.name_off = (uint32_t)s->names.size();
+    d.name_len = (uint32_t)f.name_len;
+    s->names.insert(s->names.end(), (const uint8_t*)f.name, (const uint8_t*)f.name + f.name_len);
+    d.hash = fnv1a((const uint8_t*)f.name, d.name_len);
+    d.elem_type = (int8_t)f.elem_type; d.depth = (int8_t)f.depth; d.nullable = f.nullable ? 1 : 0;
+    d.kind = (int8_t)required_kind(f.elem_type);
+    bool varlen = f.elem_type == TFR_T_STRING || f.elem_type == TFR_T_BINARY;
+    d.n_levels = (int16_t)(f.depth + (varlen ? 1 : 0));
+    d.dup_next = -1;
+    d.width = type_width(f.elem_type);
+    d.fix_slot = -1; d.var_slot = -1; d.cnt_slot = -1;
+    if (f.elem_type == TFR_T_NULL) { /* no storage beyond validity */ }
+    else if (d.n_levels == 0) { d.fix_slot = s->n_fix++; s->fix_field.push_back(i); }
+    else { d.var_slot = s->n_var++; d.cnt_slot = s->n_cnt; s->n_cnt += d.n_levels; s->var_field.push_back(i); }
+    s->fields.push_back(d);
+  }
+  // Spark refuses duplicate column names for file sources before the reader is built
+  // (SchemaUtils.checkColumnNameDuplication), so they never reach TFRecordDeserializer
+  size_t hsz = 2; while (hsz < 2 * (size_t)n_fields + 2) hsz <<= 1;
+  s->ht.assign(hsz, -1);
+  for (int32_t i = 0; i < n_fields; ++i) {
+    const DevField& d = s->fields[i];
+    size_t slot = d.hash & (hsz - 1);
+    while (s->ht[slot] >= 0) {
+      const DevField& o = s->fields[s->ht[slot]];
+      if (o.hash == d.hash && o.name_len == d.name_len && memcmp(&s->names[o.name_off], &s->names[d.name_off], d.name_len) == 0) {
+        delete s; return fail(TFR_E_INVALID_ARG, "Found duplicate column(s) in the data schema");
+      }
+      slot = (slot + 1) & (hsz - 1);
+    }
+    s->ht[slot] = i;
+  }
+  *out = s;
+  return TFR_OK;
+}
+extern "C" void tfr_schema_destroy(tfr_schema* s) { delete s; }
+extern "C" int32_t tfr_schema_num_fields(const tfr_schema* s) { return s ? (int32_t)s->fields.size() : 0; }
+
+// device copy of a schema
+struct DevSchemaBuf {
+  DevField* d_fields = nullptr; uint8_t* d_names = nullptr; int32_t* d_ht = nullptr; int32_t* d_var_field = nullptr;
+  DevSchema view{};
+  int32_t upload(const tfr_schema& s) {
+    size_t nf = s.fields.size();
+    CUDA_TRY(cudaMalloc(&d_fields, std::max<size_t>(1, nf) * sizeof(DevField)));
+    CUDA_TRY(cudaMalloc(&d_names, std::max<size_t>(1, s.names.size())));
+    CUDA_TRY(cudaMalloc(&d_ht, s.ht.size() * sizeof(int32_t)));
+    CUDA_TRY(cudaMalloc(&d_var_field, std::max<size_t>(1, s.var_field.size()) * sizeof(int32_t)));
+    if (nf) CUDA_TRY(cudaMemcpy(d_fields, s.fields.data(), nf * sizeof(DevField), cudaMemcpyHostToDevice));
+    if (!s.names.empty()) CUDA_TRY(cudaMemcpy(d_names, s.names.data(), s.names.size(), cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(d_ht, s.ht.data(), s.ht.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+    if (!s.var_field.empty()) CUDA_TRY(cudaMemcpy(d_var_field, s.var_field.data(), s.var_field.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+    view.n_fields = (int32_t)nf; view.record_type = s.record_type; view.ht_mask = (int32_t)s.ht.size() - 1;
+    view.n_fix = s.n_fix; view.n_var = s.n_var; view.n_cnt = s.n_cnt;
+    view.fields = d_fields; view.names = d_names; view.ht = d_ht;
+    return TFR_OK;
+  }
+  void free_all() { cudaFree(d_fields); cudaFree(d_names); cudaFree(d_ht); cudaFree(d_var_field); }
+};
+
+// ---------------------------------------------------------------------------------------------
+// decoder
+// ---------------------------------------------------------------------------------------------
+static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+struct HostStats {      // pinned, written by D2H copies
+  FrameResult frame;
+  DecodeSummary summary;
+  uint32_t overflow;
+  uint32_t pad[3];
+};
+
+struct tfr_decoder {
+  tfr_schema schema;
+  int device = 0;
+  uint32_t flags = 0;
+  DeviceCtx* ctx = nullptr;
+  cudaStream_t stream = nullptr;
+  DevSchemaBuf dsch;
+  // reusable device scratch
+  DevBuf in, chunks, chunk_base, rec_off, status, valid8, cnt, src, cflag, tsum, scan_scratch, ptr_tables, small;
+  // pinned host
+  void* staging = nullptr; size_t staging_cap = 0;
+  HostStats* h_stats = nullptr;
+  int64_t* h_totals = nullptr;          // [n_cnt] + null counts [nf]
+  void** h_ptr_tables = nullptr;        // pinned mirror of the device pointer tables
+  size_t h_ptr_cap = 0;
+  PinnedPool host_pool;
+};
+
+struct Segment { void* dev; size_t bytes; size_t host_off; };
+
+struct tfr_batch {
+  tfr_decoder* dec = nullptr;
+  std::atomic<int> refs{1};
+  tfr_batch_info info{};
+  std::vector<tfr_column> cols;          // device view
+  std::vector<tfr_column> host_cols;     // host view (after to_host)
+  void* dev_fixed = nullptr; size_t dev_fixed_bytes = 0;
+  void* dev_var = nullptr; size_t dev_var_bytes = 0;
+  unsigned long long* d_null_counts = nullptr;   // inside dev_fixed
+  std::vector<unsigned long long> h_null_counts_tmp;
+  void* host_copy = nullptr; size_t host_copy_bytes = 0;
+  bool null_counts_ready = false;
+  cudaEvent_t done = nullptr;
+};
+
+extern "C" int32_t tfr_decoder_create(const tfr_schema* schema, int32_t device, uint32_t flags, tfr_decoder** out) {
+  if (!schema || !out) return fail(TFR_E_INVALID_ARG, "null argument");
+  DeviceCtx* ctx = nullptr;
+  int32_t rc = get_ctx(device, &ctx);
+  if (rc) return rc;
+  CUDA_TRY(cudaSetDevice(device));
+  auto* d = new tfr_decoder;
+  d->schema = *schema; d->device = device; d->flags = flags; d->ctx = ctx;
+  CUDA_TRY(cudaStreamCreateWithFlags(&d->stream, cudaStreamNonBlocking));
+  rc = d->dsch.upload(d->schema);
+  if (rc) { delete d; return rc; }
+  TRY(d->small.ensure(4096 + (size_t)d->schema.n_cnt * 8));
+  CUDA_TRY(cudaHostAlloc((void**)&d->h_stats, sizeof(HostStats), cudaHostAllocDefault));
+  size_t nt = (size_t)d->schema.n_cnt + d->schema.fields.size() + 8;
+  CUDA_TRY(cudaHostAlloc((void**)&d->h_totals, nt * sizeof(int64_t), cudaHostAllocDefault));
+  *out = d;
+  return TFR_OK;
+}
+extern "C" void tfr_decoder_destroy(tfr_decoder* d) {
+  if (!d) return;
+  cudaSetDevice(d->device);
+  cudaStreamSynchronize(d->stream);
+  for (DevBuf* b : {&d->in, &d->chunks, &d->chunk_base, &d->rec_off, &d->status, &d->valid8, &d->cnt, &d->src, &d->cflag, &d->tsum,
+                    &d->scan_scratch, &d->ptr_tables, &d->small})
+    b->release();
+  d->dsch.free_all();
+  if (d->staging) cudaFreeHost(d->staging);
+  cudaFreeHost(d->h_stats); cudaFreeHost(d->h_totals);
+  if (d->h_ptr_tables) cudaFreeHost(d->h_ptr_tables);
+  d->host_pool.release_all();
+  cudaStreamDestroy(d->stream);
+  delete d;
+}
+extern "C" int32_t tfr_decoder_staging(tfr_decoder* d, size_t min_bytes, void** host_ptr, size_t* capacity) {
+  if (!d || !host_ptr) return fail(TFR_E_INVALID_ARG, "null argument");
+  CUDA_TRY(cudaSetDevice(d->device));
+  if (d->staging_cap < min_bytes) {
+    CUDA_TRY(cudaStreamSynchronize(d->stream));
+    if (d->staging) cudaFreeHost(d->staging);
+    d->staging = nullptr; d->staging_cap = 0;
+    size_t cap = align_up(std::max<size_t>(min_bytes, 1 << 20), 1 << 20);
+    CUDA_TRY(cudaHostAlloc(&d->staging, cap, cudaHostAllocDefault));
+    d->staging_cap = cap;
+  }
+  *host_ptr = d->staging;
+  if (capacity) *capacity = d->staging_cap;
+  return TFR_OK;
+}
+extern "C" int32_t tfr_decoder_stream(tfr_decoder* d, void** s) { if (!d || !s) return TFR_E_INVALID_ARG; *s = d->stream; return TFR_OK; }
+
+static int32_t frame_stop_to_error(uint32_t stop, bool is_final) {
+  switch (stop) {
+    case FS_BAD_CRC: return TFR_E_CRC_LENGTH;
+    case FS_TOO_LARGE: return TFR_E_RECORD_TOO_LARGE;
+    case FS_PART_HDR: case FS_PART_REC: return is_final ? TFR_E_TRUNCATED : TFR_OK;
+    default: return TFR_OK;       // FS_EOF, FS_STRAY (EOFException on the length bytes is a clean EOF)
+  }
+}
+
+static uint32_t pick_chunk_bytes(size_t nbytes, int sm_count) {
+  // enough chunks to give every resident warp work, large enough to amortise the candidate search
+  size_t want = (size_t)sm_count * 64;
+  size_t c = 4096;
+  while (c < 65536 && nbytes / c > want * 4) c <<= 1;
+  return (uint32_t)c;
+}
+
+extern "C" int32_t tfr_decode(tfr_decoder* d, const void* data, size_t nbytes, int32_t data_on_device, int32_t is_final, tfr_batch** out,
+                              size_t* consumed) {
+  if (!d || !out || (nbytes && !data)) return fail(TFR_E_INVALID_ARG, "null argument");
+  if (nbytes >= (1ull << 31)) return fail(TFR_E_BATCH_TOO_LARGE, "tfr_decode: a batch must be smaller than 2 GiB; split the file at record boundaries");
+  CUDA_TRY(cudaSetDevice(d->device));
+  cudaStream_t st = d->stream;
+  const tfr_schema& S = d->schema;
+  const uint32_t nf = (uint32_t)S.fields.size();
+  const uint32_t verify = (d->flags & TFR_F_VERIFY_CRC) ? 1u : 0u;
+  auto* b = new tfr_batch;
+  b->dec = d;
+  b->info.error_row = -1; b->info.error_field = -1;
+  std::unique_ptr<tfr_batch, void (*)(tfr_batch*)> guard(b, [](tfr_batch* x) { tfr_batch_release(x); });
+
+  // ---- input ----
+  const uint8_t* d_data = (const uint8_t*)data;
+  if (!data_on_device && nbytes) {
+    TRY(d->in.ensure(align_up(nbytes + 16, 256)));
+    CUDA_TRY(cudaMemcpyAsync(d->in.p, data, nbytes, cudaMemcpyHostToDevice, st));
+    d_data = (const uint8_t*)d->in.p;
+  }
+  // ---- K1: record boundaries ----
+  uint32_t n = 0;
+  FrameResult fr{};
+  fr.stop = FS_EOF;
+  uint32_t n_chunks = 0, chunk_bytes = 0;
+  if (nbytes) {
+    chunk_bytes = pick_chunk_bytes(nbytes, d->ctx->sm_count);
+    n_chunks = (uint32_t)((nbytes + chunk_bytes - 1) / chunk_bytes);
+    TRY(d->chunks.ensure((size_t)n_chunks * sizeof(ChunkInfo)));
+    TRY(d->chunk_base.ensure(((size_t)n_chunks + 1) * sizeof(uint32_t)));
+    FrameResult* d_fr = (FrameResult*)d->small.p;
+    FrameResult init{}; init.first_bad = 0xffffffffu;
+    d->h_stats->frame = init;
+    CUDA_TRY(cudaMemcpyAsync(d_fr, &d->h_stats->frame, sizeof(FrameResult), cudaMemcpyHostToDevice, st));
+    uint32_t grid = std::min<uint32_t>((n_chunks + 7) / 8, (uint32_t)d->ctx->sm_count * 8);
+    frame_scan_kernel<<<grid, 256, 0, st>>>(d_data, (uint32_t)nbytes, chunk_bytes, n_chunks, verify, d->ctx->d_tabs, (ChunkInfo*)d->chunks.p);
+    frame_check_kernel<<<(n_chunks + 255) / 256, 256, 0, st>>>((const ChunkInfo*)d->chunks.p, n_chunks, d_fr);
+    frame_repair_kernel<<<1, 32, 0, st>>>(d_data, (uint32_t)nbytes, chunk_bytes, n_chunks, verify, d->ctx->d_tabs, (ChunkInfo*)d->chunks.p, d_fr);
+    frame_finish_kernel<<<1, 1024, 0, st>>>((const ChunkInfo*)d->chunks.p, n_chunks, (uint32_t)nbytes, (uint32_t*)d->chunk_base.p, d_fr);
+    CUDA_TRY(cudaMemcpyAsync(&d->h_stats->frame, d_fr, sizeof(FrameResult), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));                       // sync #1: number of records
+    CUDA_TRY(cudaGetLastError());
+    fr = d->h_stats->frame;
+    n = fr.n_records;
+  }
+  int32_t frame_err = frame_stop_to_error(fr.stop, is_final != 0);
+  size_t used = nbytes;
+  if (nbytes) {
+    if (frame_err) used = fr.stop_pos;
+    else if (fr.stop == FS_EOF) used = nbytes;
+    else if (fr.stop == FS_STRAY) used = is_final ? nbytes : fr.stop_pos;
+    else used = fr.stop_pos;                                   // partial tail of a non-final block is carried over
+  }
+  b->info.n_records = n; b->info.frame_repairs = (int32_t)fr.repairs;
+  if (consumed) *consumed = used;
+  b->info.consumed_bytes = (int64_t)used;
+
+  // ---- buffers that depend on n ----
+  const uint32_t nb_stride = (uint32_t)align_up(((size_t)n + 7) / 8 + 1, 64);
+  std::vector<size_t> fix_off(S.n_fix), off0_off(S.n_var);
+  size_t fixed_bytes = 0;
+  size_t bitmaps_off = 0; fixed_bytes += align_up((size_t)nb_stride * std::max<uint32_t>(nf, 1), 256);
+  size_t nullc_off = fixed_bytes; fixed_bytes += align_up(sizeof(unsigned long long) * std::max<uint32_t>(nf, 1), 256);
+  for (int i = 0; i < S.n_fix; ++i) { fix_off[i] = fixed_bytes; fixed_bytes += align_up((size_t)n * S.fields[S.fix_field[i]].width + 8, 256); }
+  for (int v = 0; v < S.n_var; ++v) { off0_off[v] = fixed_bytes; fixed_bytes += align_up(((size_t)n + 1) * 4, 256); }
+  CUDA_TRY(cudaMallocAsync(&b->dev_fixed, fixed_bytes, st));
+  b->dev_fixed_bytes = fixed_bytes;
+  uint8_t* fx = (uint8_t*)b->dev_fixed;
+  b->d_null_counts = (unsigned long long*)(fx + nullc_off);
+  CUDA_TRY(cudaMemsetAsync(fx + nullc_off, 0, sizeof(unsigned long long) * std::max<uint32_t>(nf, 1), st));
+  for (int v = 0; v < S.n_var; ++v) if (n == 0) CUDA_TRY(cudaMemsetAsync(fx + off0_off[v], 0, 4, st));
+
+  // pointer tables (device arrays of pointers used by the kernels), staged through pinned memory
+  const size_t n_ptr = (size_t)S.n_fix + (size_t)S.n_cnt + (size_t)S.n_var * 3 + (size_t)S.n_var + 8;
+  if (d->h_ptr_cap < n_ptr) {
+    if (d->h_ptr_tables) cudaFreeHost(d->h_ptr_tables);
+    CUDA_TRY(cudaHostAlloc((void**)&d->h_ptr_tables, n_ptr * sizeof(void*), cudaHostAllocDefault));
+    d->h_ptr_cap = n_ptr;
+  }
+  TRY(d->ptr_tables.ensure(n_ptr * sizeof(void*)));
+  void** hp = d->h_ptr_tables;
+  void** dp = (void**)d->ptr_tables.p;
+  void** t_fix = hp;                    void** dt_fix = dp;
+  void** t_scan = hp + S.n_fix;         void** dt_scan = dp + S.n_fix;
+  void** t_offs = t_scan + S.n_cnt;     void** dt_offs = dt_scan + S.n_cnt;
+  void** t_vals = t_offs + S.n_var * 3; void** dt_vals = dt_offs + S.n_var * 3;
+
+  int64_t* totals = d->h_totals;                      // [n_cnt]
+  DecodeSummary sum{}; sum.first_err_row = 0xffffffffu; sum.n_eff = n;
+  uint32_t n_eff = n;
+  if (n > 0) {
+    TRY(d->rec_off.ensure(((size_t)n + 1) * 4));
+    uint32_t grid = std::min<uint32_t>((n_chunks + 7) / 8, (uint32_t)d->ctx->sm_count * 8);
+    frame_emit_kernel<<<grid, 256, 0, st>>>(d_data, (const ChunkInfo*)d->chunks.p, (const uint32_t*)d->chunk_base.p, n_chunks,
+                                            (const FrameResult*)d->small.p, (uint32_t*)d->rec_off.p);
+    TRY(d->status.ensure((size_t)n * 4));
+    TRY(d->valid8.ensure((size_t)n * std::max<uint32_t>(nf, 1) + 8));
+    TRY(d->cnt.ensure((size_t)n * std::max<int>(S.n_cnt, 1) * 4));
+    TRY(d->src.ensure((size_t)n * std::max<int>(S.n_var, 1) * 4));
+    TRY(d->cflag.ensure((size_t)n * std::max<int>(S.n_var, 1)));
+    // scan outputs: level 0 -> the Arrow offsets in dev_fixed, deeper levels -> scratch
+    size_t deep = 0;
+    for (int v = 0; v < S.n_var; ++v) deep += (size_t)(S.fields[S.var_field[v]].n_levels - 1);
+    TRY(d->scan_scratch.ensure(deep * align_up(((size_t)n + 1) * 4, 256) + 256));
+    size_t so = 0;
+    for (int v = 0; v < S.n_var; ++v) {
+      const DevField& fd = S.fields[S.var_field[v]];
+      t_scan[fd.cnt_slot] = fx + off0_off[v];
+      for (int l = 1; l < fd.n_levels; ++l) { t_scan[fd.cnt_slot + l] = (uint8_t*)d->scan_scratch.p + so; so += align_up(((size_t)n + 1) * 4, 256); }
+    }
+    for (int i = 0; i < S.n_fix; ++i) t_fix[i] = fx + fix_off[i];
+    CUDA_TRY(cudaMemcpyAsync(dp, hp, ((size_t)S.n_fix + S.n_cnt) * sizeof(void*), cudaMemcpyHostToDevice, st));
+
+    DecodeArgs A{};
+    A.data = d_data; A.rec_off = (const uint32_t*)d->rec_off.p; A.n = n; A.verify = verify;
+    A.sch = d->dsch.view; A.tabs = d->ctx->d_tabs;
+    A.status = (uint32_t*)d->status.p; A.valid8 = (uint8_t*)d->valid8.p; A.fix_values = (void* const*)dt_fix;
+    A.cnt = (uint32_t*)d->cnt.p; A.src = (uint32_t*)d->src.p; A.cflag = (uint8_t*)d->cflag.p;
+    const uint32_t warps = 8;
+    size_t smem1 = CRC_SMEM_WORDS * 4 + (size_t)warps * ((nf + 3) & ~3u);
+    uint32_t g1 = std::min<uint32_t>((n + warps - 1) / warps, (uint32_t)d->ctx->sm_count * 16);
+    decode_pass1_kernel<<<g1, warps * 32, smem1, st>>>(A);
+
+    DecodeSummary* d_sum = (DecodeSummary*)((uint8_t*)d->small.p + 256);
+    uint32_t* d_overflow = (uint32_t*)((uint8_t*)d->small.p + 512);
+    int64_t* d_totals = (int64_t*)((uint8_t*)d->small.p + 1024);
+    d->h_stats->summary = sum; d->h_stats->overflow = 0;
+    CUDA_TRY(cudaMemcpyAsync(d_sum, &d->h_stats->summary, sizeof(DecodeSummary), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemsetAsync(d_overflow, 0, 4, st));
+    first_error_kernel<<<std::min<uint32_t>((n + 255) / 256, 1024), 256, 0, st>>>(A.status, n, d_sum);
+    if (S.n_cnt > 0) {
+      uint32_t n_tiles = (n + SCAN_TILE - 1) / SCAN_TILE;
+      TRY(d->tsum.ensure(((size_t)S.n_cnt * n_tiles + S.n_cnt) * 8 + 64));
+      uint64_t* tsum = (uint64_t*)d->tsum.p;
+      uint64_t* traw = tsum + (size_t)S.n_cnt * n_tiles;
+      scan_tile_sums_kernel<<<dim3(n_tiles, S.n_cnt), SCAN_THREADS, 0, st>>>(A.cnt, n, n_tiles, tsum);
+      scan_tile_bases_kernel<<<S.n_cnt, 1024, 0, st>>>(tsum, n_tiles, traw, d_overflow);
+      scan_apply_kernel<<<dim3(n_tiles, S.n_cnt), SCAN_THREADS, 0, st>>>(A.cnt, n, n_tiles, tsum, traw, (int32_t* const*)dt_scan);
+    }
+    summary_kernel<<<1, 256, 0, st>>>(A.status, n, d_sum, (const int32_t* const*)dt_scan, (uint32_t)S.n_cnt, d_totals);
+    CUDA_TRY(cudaMemcpyAsync(&d->h_stats->summary, d_sum, sizeof(DecodeSummary), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(&d->h_stats->overflow, d_overflow, 4, cudaMemcpyDeviceToHost, st));
+    if (S.n_cnt) CUDA_TRY(cudaMemcpyAsync(totals, d_totals, (size_t)S.n_cnt * 8, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));                       // sync #2: totals of the variable-width columns
+    CUDA_TRY(cudaGetLastError());
+    sum = d->h_stats->summary;
+    n_eff = sum.n_eff;
+    if (d->h_stats->overflow) {
+      // a prefix beyond int32 somewhere in the batch: only fatal if it is inside the delivered rows
+      for (int a = 0; a < S.n_cnt; ++a) if (totals[a] < 0 || totals[a] > 0x7fffffffLL) return fail(TFR_E_BATCH_TOO_LARGE, "Arrow int32 offsets overflow; decode smaller blocks");
+    }
+    // ---- variable-width outputs ----
+    std::vector<size_t> lvl_off((size_t)S.n_var * 3, 0), val_off(S.n_var, 0);
+    size_t var_bytes = 0;
+    for (int v = 0; v < S.n_var; ++v) {
+      const DevField& fd = S.fields[S.var_field[v]];
+      for (int l = 1; l < fd.n_levels; ++l) { lvl_off[v * 3 + l] = var_bytes; var_bytes += align_up(((size_t)totals[fd.cnt_slot + l - 1] + 1) * 4, 256); }
+      val_off[v] = var_bytes; var_bytes += align_up((size_t)totals[fd.cnt_slot + fd.n_levels - 1] * fd.width + 8, 256);
+    }
+    if (var_bytes) CUDA_TRY(cudaMallocAsync(&b->dev_var, var_bytes, st));
+    b->dev_var_bytes = var_bytes;
+    uint8_t* vx = (uint8_t*)b->dev_var;
+    for (int v = 0; v < S.n_var; ++v) {
+      const DevField& fd = S.fields[S.var_field[v]];
+      t_offs[v * 3 + 0] = fx + off0_off[v];
+      for (int l = 1; l < 3; ++l) t_offs[v * 3 + l] = l < fd.n_levels ? vx + lvl_off[v * 3 + l] : nullptr;
+      for (int l = 1; l < fd.n_levels; ++l) CUDA_TRY(cudaMemsetAsync(vx + lvl_off[v * 3 + l], 0, 4, st));
+      t_vals[v] = vx + val_off[v];
+    }
+    CUDA_TRY(cudaMemcpyAsync(dt_offs, t_offs, ((size_t)S.n_var * 4) * sizeof(void*), cudaMemcpyHostToDevice, st));
+    A.n_eff = n_eff; A.scan = (const int32_t* const*)dt_scan; A.offs = (int32_t* const*)dt_offs; A.var_values = (void* const*)dt_vals;
+    A.var_field = d->dsch.d_var_field;
+    if (n_eff > 0 && S.n_var > 0) {
+      uint32_t g2 = std::min<uint32_t>((n_eff + warps - 1) / warps, (uint32_t)d->ctx->sm_count * 16);
+      decode_pass2_kernel<<<g2, warps * 32, 0, st>>>(A);
+    }
+    if (n_eff > 0 && nf > 0) {
+      uint32_t nbytes_bm = (n_eff + 7) / 8;
+      dim3 g((nbytes_bm + 255) / 256, nf);
+      g.x = std::min<uint32_t>(g.x, 4096);
+      pack_validity_kernel<<<g, 256, 0, st>>>(A.valid8, n, n_eff, nf, nb_stride, fx + bitmaps_off, b->d_null_counts);
+    }
+    // device column views
+    b->cols.resize(nf);
+    int64_t out_bytes = 0;
+    for (uint32_t f = 0; f < nf; ++f) {
+      const DevField& fd = S.fields[f];
+      tfr_column c{};
+      c.elem_type = fd.elem_type; c.depth = fd.depth; c.n_levels = fd.n_levels; c.value_width = fd.width;
+      c.n_rows = n_eff; c.validity = fx + bitmaps_off + (size_t)f * nb_stride;
+      out_bytes += (n_eff + 7) / 8;
+      if (fd.fix_slot >= 0) { c.values = fx + fix_off[fd.fix_slot]; c.n_values = n_eff; out_bytes += (int64_t)n_eff * fd.width; }
+      else if (fd.var_slot >= 0) {
+        int v = fd.var_slot;
+        c.offsets[0] = (int32_t*)(fx + off0_off[v]); c.n_offsets[0] = (int64_t)n_eff + 1;
+        for (int l = 1; l < fd.n_levels; ++l) { c.offsets[l] = (int32_t*)(vx + lvl_off[v * 3 + l]); c.n_offsets[l] = totals[fd.cnt_slot + l - 1] + 1; }
+        c.values = vx + val_off[v]; c.n_values = totals[fd.cnt_slot + fd.n_levels - 1];
+        for (int l = 0; l < fd.n_levels; ++l) out_bytes += c.n_offsets[l] * 4;
+        out_bytes += c.n_values * fd.width;
+      }
+      b->cols[f] = c;
+    }
+    b->info.out_bytes = out_bytes;
+  } else {
+    // no complete record: empty columns
+    b->cols.resize(nf);
+    for (uint32_t f = 0; f < nf; ++f) {
+      const DevField& fd = S.fields[f];
+      tfr_column c{};
+      c.elem_type = fd.elem_type; c.depth = fd.depth; c.n_levels = fd.n_levels; c.value_width = fd.width;
+      c.validity = fx + bitmaps_off + (size_t)f * nb_stride;
+      if (fd.var_slot >= 0) { c.offsets[0] = (int32_t*)(fx + off0_off[fd.var_slot]); c.n_offsets[0] = 1; }
+      if (fd.fix_slot >= 0) c.values = fx + fix_off[fd.fix_slot];
+      // deeper levels of an empty column: a single zero offset, served from the level-0 array (also a single 0)
+      for (int l = 1; l < fd.n_levels; ++l) { c.offsets[l] = c.offsets[0]; c.n_offsets[l] = 1; }
+      b->cols[f] = c;
+    }
+  }
+  // ---- first error in record order: per-row status (pass 1) or the framing stop at row n ----
+  b->info.n_rows = n_eff;
+  if (n > 0 && sum.first_err_row != 0xffffffffu) {
+    b->info.error_code = -(int32_t)(sum.first_err_status & 0xff);
+    b->info.error_row = sum.first_err_row;
+    b->info.error_field = (int32_t)(sum.first_err_status >> 8) - 1;
+  } else if (frame_err) {
+    b->info.error_code = frame_err; b->info.error_row = n; b->info.error_field = -1;
+  }
+  CUDA_TRY(cudaEventCreateWithFlags(&b->done, cudaEventDisableTiming));
+  CUDA_TRY(cudaEventRecord(b->done, st));
+  CUDA_TRY(cudaGetLastError());
+  guard.release();
+  *out = b;
+  return TFR_OK;
+}
+
+extern "C" int32_t tfr_batch_wait(tfr_batch* b) {
+  if (!b) return fail(TFR_E_INVALID_ARG, "null batch");
+  CUDA_TRY(cudaSetDevice(b->dec->device));
+  if (b->done) CUDA_TRY(cudaEventSynchronize(b->done));
+  if (!b->null_counts_ready) {
+    size_t nf = b->cols.size();
+    if (nf && b->info.n_rows > 0) {
+      b->h_null_counts_tmp.resize(nf);
+      CUDA_TRY(cudaMemcpy(b->h_null_counts_tmp.data(), b->d_null_counts, nf * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+      for (size_t f = 0; f < nf; ++f) b->cols[f].null_count = (int64_t)b->h_null_counts_tmp[f];
+    }
+    b->null_counts_ready = true;
+  }
+  return TFR_OK;
+}
+extern "C" int32_t tfr_batch_status(tfr_batch* b, tfr_batch_info* out) {
+  if (!b || !out) return fail(TFR_E_INVALID_ARG, "null argument");
+  *out = b->info;
+  return TFR_OK;
+}
+extern "C" int32_t tfr_batch_num_columns(tfr_batch* b) { return b ? (int32_t)b->cols.size() : 0; }
+extern "C" int32_t tfr_batch_columns(tfr_batch* b, tfr_column* out, int32_t n) {
+  if (!b || !out || n < (int32_t)b->cols.size()) return fail(TFR_E_INVALID_ARG, "bad argument");
+  int32_t rc = tfr_batch_wait(b);
+  if (rc) return rc;
+  std::copy(b->cols.begin(), b->cols.end(), out);
+  return TFR_OK;
+}
+
+// D2H of both output blocks into one pinned buffer, then host views with the same relative layout
+extern "C" int32_t tfr_batch_to_host(tfr_batch* b, tfr_column* out, int32_t n) {
+  if (!b || n < (int32_t)b->cols.size()) return fail(TFR_E_INVALID_ARG, "bad argument");
+  tfr_decoder* d = b->dec;
+  CUDA_TRY(cudaSetDevice(d->device));
+  if (!b->host_copy) {
+    size_t total = align_up(b->dev_fixed_bytes, 256) + align_up(b->dev_var_bytes, 256) + 256;
+    void* h = d->host_pool.acquire(total);
+    if (!h) return fail(TFR_E_OOM, "pinned host allocation failed");
+    b->host_copy = h; b->host_copy_bytes = total;
+    uint8_t* hb = (uint8_t*)h;
+    if (b->dev_fixed_bytes) CUDA_TRY(cudaMemcpyAsync(hb, b->dev_fixed, b->dev_fixed_bytes, cudaMemcpyDeviceToHost, d->stream));
+    if (b->dev_var_bytes) CUDA_TRY(cudaMemcpyAsync(hb + align_up(b->dev_fixed_bytes, 256), b->dev_var, b->dev_var_bytes, cudaMemcpyDeviceToHost, d->stream));
+    CUDA_TRY(cudaStreamSynchronize(d->stream));
+    int32_t rc = tfr_batch_wait(b);
+    if (rc) return rc;
+    auto xl = [&](void* p) -> void* {
+      if (!p) return nullptr;
+      uint8_t* q = (uint8_t*)p;
+      uint8_t* f0 = (uint8_t*)b->dev_fixed; uint8_t* v0 = (uint8_t*)b->dev_var;
+      if (f0 && q >= f0 && q < f0 + b->dev_fixed_bytes) return hb + (q - f0);
+      if (v0 && q >= v0 && q < v0 + b->dev_var_bytes) return hb + align_up(b->dev_fixed_bytes, 256) + (q - v0);
+      return nullptr;
+    };
+    b->host_cols = b->cols;
+    for (auto& c : b->host_cols) {
+      c.validity = (uint8_t*)xl(c.validity);
+      for (int l = 0; l < 3; ++l) c.offsets[l] = (int32_t*)xl(c.offsets[l]);
+      c.values = xl(c.values);
+    }
+  }
+  if (out) std::copy(b->host_cols.begin(), b->host_cols.end(), out);
+  return TFR_OK;
+}
+
+extern "C" void tfr_batch_release(tfr_batch* b) {
+  if (!b) return;
+  if (b->refs.fetch_sub(1) != 1) return;
+  tfr_decoder* d = b->dec;
+  cudaSetDevice(d->device);
+  if (b->dev_fixed) cudaFreeAsync(b->dev_fixed, d->stream);
+  if (b->dev_var) cudaFreeAsync(b->dev_var, d->stream);
+  if (b->host_copy) d->host_pool.give_back(b->host_copy);
+  if (b->done) cudaEventDestroy(b->done);
+  delete b;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Arrow C Data Interface export (arrow/c/abi.h structs restated in host_util.h)
+// ---------------------------------------------------------------------------------------------
+struct ExportPriv { tfr_batch* batch; std::vector<const void*> buffers; std::vector<ArrowArray*> children; ArrowArray* child_storage = nullptr; };
+
+static void release_array(ArrowArray* a) {
+  if (!a || !a->release) return;
+  auto* p = (ExportPriv*)a->private_data;
+  for (int64_t i = 0; i < a->n_children; ++i) {
+    if (a->children[i]->release) a->children[i]->release(a->children[i]);
+    delete a->children[i];
+  }
+  if (p) { if (p->batch) tfr_batch_release(p->batch); delete p; }
+  a->release = nullptr;
+}
+static void release_schema(ArrowSchema* s) {
+  if (!s || !s->release) return;
+  for (int64_t i = 0; i < s->n_children; ++i) {
+    if (s->children[i]->release) s->children[i]->release(s->children[i]);
+    delete s->children[i];
+  }
+  delete[] s->children;
+  free((void*)s->name);
+  s->release = nullptr;
+}
+static const char* leaf_format(int t) {
+  switch (t) {
+    case TFR_T_INT32: return "i"; case TFR_T_INT64: return "l"; case TFR_T_FLOAT32: return "f";
+    case TFR_T_FLOAT64: case TFR_T_DECIMAL: return "g"; case TFR_T_STRING: return "u"; case TFR_T_BINARY: return "z";
+    default: return "n";
+  }
+}
+static void build_schema(ArrowSchema* s, const char* name, int elem_type, int depth) {
+  memset(s, 0, sizeof *s);
+  s->name = strdup(name); s->flags = 2 /*ARROW_FLAG_NULLABLE*/; s->release = release_schema;
+  if (depth == 0) { s->format = leaf_format(elem_type); return; }
+  s->format = "+l";
+  s->n_children = 1; s->children = new ArrowSchema*[1];
+  s->children[0] = new ArrowSchema;
+  build_schema(s->children[0], "item", elem_type, depth - 1);
+}
+// level: which offsets level this list node uses; leaves use the last level for utf8/binary
+static void build_array(ArrowArray* a, const tfr_column& c, int level, int64_t length, tfr_batch* owner) {
+  memset(a, 0, sizeof *a);
+  auto* p = new ExportPriv;
+  p->batch = owner;
+  if (owner) owner->refs.fetch_add(1);
+  a->private_data = p; a->release = release_array; a->length = length; a->offset = 0;
+  const bool varlen = c.elem_type == TFR_T_STRING || c.elem_type == TFR_T_BINARY;
+  const void* validity = level == 0 ? c.validity : nullptr;
+  a->null_count = level == 0 ? c.null_count : 0;
+  if (level < c.depth) {                 // list node
+    p->buffers = {validity, c.offsets[level]};
+    a->n_buffers = 2;
+    a->n_children = 1;
+    p->children.resize(1); p->children[0] = new ArrowArray;
+    a->children = p->children.data();
+    int64_t child_len = level + 1 < c.n_levels ? c.n_offsets[level + 1] - 1 : c.n_values;
+    build_array(a->children[0], c, level + 1, child_len, nullptr);
+  } else if (c.elem_type == TFR_T_NULL) {
+    a->n_buffers = 0; a->null_count = length;
+  } else if (varlen) {
+    p->buffers = {validity, c.offsets[c.n_levels - 1], c.values};
+    a->n_buffers = 3;
+  } else {
+    p->buffers = {validity, c.values};
+    a->n_buffers = 2;
+  }
+  a->buffers = p->buffers.data();
+}
+
+extern "C" int32_t tfr_batch_export_arrow_host(tfr_batch* b, int32_t column, void* arrow_array, void* arrow_schema) {
+  if (!b || !arrow_array || !arrow_schema || column < 0 || column >= (int32_t)b->cols.size()) return fail(TFR_E_INVALID_ARG, "bad argument");
+  int32_t rc = tfr_batch_to_host(b, nullptr, (int32_t)b->cols.size());
+  if (rc) return rc;
+  const tfr_column& c = b->host_cols[column];
+  const tfr_schema& S = b->dec->schema;
+  std::string nm((const char*)&S.names[S.fields[column].name_off], S.fields[column].name_len);
+  build_schema((ArrowSchema*)arrow_schema, nm.c_str(), c.elem_type, c.depth);
+  build_array((ArrowArray*)arrow_array, c, 0, c.n_rows, b);
+  return TFR_OK;
+}
+extern "C" int32_t tfr_batch_export_arrow_device(tfr_batch* b, int32_t column, void* arrow_device_array, void* arrow_schema) {
+  if (!b || !arrow_device_array || !arrow_schema || column < 0 || column >= (int32_t)b->cols.size()) return fail(TFR_E_INVALID_ARG, "bad argument");
+  int32_t rc = tfr_batch_wait(b);
+  if (rc) return rc;
+  const tfr_column& c = b->cols[column];
+  const tfr_schema& S = b->dec->schema;
+  std::string nm((const char*)&S.names[S.fields[column].name_off], S.fields[column].name_len);
+  build_schema((ArrowSchema*)arrow_schema, nm.c_str(), c.elem_type, c.depth);
+  auto* da = (ArrowDeviceArray*)arrow_device_array;
+  memset(da, 0, sizeof *da);
+  build_array(&da->array, c, 0, c.n_rows, b);
+  da->device_id = b->dec->device; da->device_type = 2 /*ARROW_DEVICE_CUDA*/; da->sync_event = nullptr;   // batch already waited
+  return TFR_OK;
+}
+
+#include "api_encode.inc"

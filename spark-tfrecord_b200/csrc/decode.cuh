@@ -1,0 +1,697 @@
+// decode.cuh -- K2/K3: CRC-32C verify + protobuf wire parse of Example / SequenceExample +
+// schema-driven scatter into Arrow-layout columns.
+//
+// Replaces, per record, tensorflow-hadoop's payload CRC check, Example.parseFrom /
+// SequenceExample.parseFrom (M/TFRecordFileReader.scala:73,76) and deserializeExample /
+// deserializeSequenceExample (M/TFRecordDeserializer.scala:21-61, coercions :68-232).
+//
+// One warp owns one record.
+//   pass 1 (decode_pass1_kernel): warp-parallel CRC of the payload; the map entries of Features are
+//     discovered by a uniform hop over `0A len` fields, then parsed one entry per lane (32 at a time):
+//     full validation of the wire format (every feature, in the schema or not, exactly like a full
+//     protobuf parse), key lookup through a hash of the schema names, protobuf merge semantics
+//     (duplicate key -> last wins, oneof switch discards, same kind concatenates, packed and unpacked
+//     mixed), the reference's coercion/null rules, fixed-width scalars written directly, element and
+//     byte counts + the source offset of each variable-width cell written to scratch.
+//   scan: the counts are prefix-summed into Arrow offsets (scan.cuh).
+//   pass 2 (decode_pass2_kernel): one lane per variable-width cell copies/decodes its values to
+//     their final place (canonical cells straight from the packed payload, everything else through a
+//     general two-walk emitter that reproduces the merge semantics).
+#pragma once
+#include "common.cuh"
+
+// cell flags (pass 1 -> pass 2)
+enum { CF_CANON = 0, CF_GENERAL = 1, CF_FLIST = 2 };
+
+struct DecodeArgs {
+  const uint8_t* data;        // framed bytes (device)
+  const uint32_t* rec_off;    // [n+1]
+  uint32_t n;                 // records to process
+  uint32_t verify;
+  DevSchema sch;
+  const CrcTables* tabs;
+  // pass-1 outputs / pass-2 inputs
+  uint32_t* status;           // [n]
+  uint8_t* valid8;            // [nf][n]
+  void* const* fix_values;    // [n_fix] typed value arrays
+  uint32_t* cnt;              // [n_cnt][n]
+  uint32_t* src;              // [n_var][n]
+  uint8_t* cflag;             // [n_var][n]
+  // pass-2 only
+  uint32_t n_eff;             // rows to emit
+  const int32_t* const* scan; // [n_cnt] exclusive prefix arrays (n+1 entries); level 0 ones are the Arrow offsets[0]
+  int32_t* const* offs;       // [n_var*3] Arrow offsets arrays per level (level 0 == scan)
+  void* const* var_values;    // [n_var] leaf value buffers
+  const int32_t* var_field;   // [n_var] schema field of each var slot
+};
+
+// ---------------------------------------------------------------------------------------------
+// Feature accumulation state (one map-entry value, possibly merged from several occurrences)
+// ---------------------------------------------------------------------------------------------
+struct FeatAcc {
+  uint32_t kind;        // K_*
+  uint32_t n;           // elements in the final run
+  uint32_t nbytes;      // BYTES: sum of output lengths (java-transcoded when want_java) of the final run
+  uint32_t first_len;   // BYTES: output length of the first element of the final run
+  uint64_t first;       // INT64: value; FLOAT: bits; BYTES: batch offset of the first element's length varint
+  uint32_t src;         // batch offset of the canonical payload (packed data / BytesList body)
+  uint32_t nseg;        // value-carrying fields in the final run (FLOAT/INT64)
+  uint32_t run_occ;     // kind-field occurrences in the final run
+  bool simple;          // no unpacked / unknown fields seen in the final run
+};
+__device__ __forceinline__ void acc_reset(FeatAcc& a, uint32_t kind) {
+  a.kind = kind; a.n = 0; a.nbytes = 0; a.first_len = 0; a.first = 0; a.src = 0; a.nseg = 0; a.run_occ = 0; a.simple = true;
+}
+__device__ __forceinline__ bool acc_canonical(const FeatAcc& a) {
+  if (a.n == 0) return true;
+  if (a.kind == K_BYTES) return a.run_occ <= 1 && a.simple;
+  return a.nseg <= 1 && a.simple;
+}
+
+__device__ __forceinline__ uint32_t out_len_bytes(const uint8_t* p, uint32_t l, bool want_java) {
+  if (!want_java || all_ascii(p, l)) return l;
+  return java_utf8_transcode(p, l, nullptr);
+}
+
+// One occurrence of a oneof member of Feature: validates the list message and folds it into `a`.
+__device__ __forceinline__ bool list_scan(uint32_t kind, Cur c, FeatAcc& a, bool want_java, const uint8_t* base) {
+  if (kind != a.kind) acc_reset(a, kind);
+  a.run_occ++;
+  if (kind == K_BYTES && a.run_occ == 1) a.src = (uint32_t)(c.p - base);
+  for (;;) {
+    uint32_t tag;
+    if (!rd_tag(c, tag)) return false;
+    if (tag == 0) return true;
+    if (kind == K_BYTES && tag == 0x0A) {
+      const uint8_t* lp = c.p;
+      uint32_t l;
+      if (!rd_len(c, l)) return false;
+      uint32_t ol = out_len_bytes(c.p, l, want_java);
+      if (a.n == 0) { a.first = (uint64_t)(lp - base); a.first_len = ol; }
+      a.n++; a.nbytes += ol;
+      c.p += l;
+    } else if (kind == K_FLOAT && tag == 0x0A) {
+      uint32_t l;
+      if (!rd_len(c, l)) return false;
+      if (l & 3) return false;                       // readFloat past the limit: truncatedMessage
+      if (l) {
+        if (a.n == 0) a.first = load_u32_unaligned(c.p);
+        a.nseg++; a.src = (uint32_t)(c.p - base);
+        a.n += l >> 2;
+      }
+      c.p += l;
+    } else if (kind == K_FLOAT && tag == 0x0D) {
+      if (c.end - c.p < 4) return false;
+      if (a.n == 0) a.first = load_u32_unaligned(c.p);
+      a.nseg++; a.simple = false; a.n++;
+      c.p += 4;
+    } else if (kind == K_INT64 && tag == 0x0A) {
+      uint32_t l;
+      if (!rd_len(c, l)) return false;
+      if (l) {
+        Cur pk{c.p, c.p + l};
+        a.nseg++; a.src = (uint32_t)(c.p - base);
+        while (pk.p < pk.end) {
+          uint64_t v;
+          if (!rd_varint64(pk, v)) return false;
+          if (a.n == 0) a.first = v;
+          a.n++;
+        }
+      }
+      c.p += l;
+    } else if (kind == K_INT64 && tag == 0x08) {
+      uint64_t v;
+      if (!rd_varint64(c, v)) return false;
+      if (a.n == 0) a.first = v;
+      a.nseg++; a.simple = false; a.n++;
+    } else {
+      if (!skip_field(c, tag)) return false;
+      a.simple = false;
+    }
+  }
+}
+// Feature message body merged into `a` (Feature.Builder.mergeFrom)
+__device__ __forceinline__ bool feature_scan(Cur c, FeatAcc& a, bool want_java, const uint8_t* base) {
+  for (;;) {
+    uint32_t tag;
+    if (!rd_tag(c, tag)) return false;
+    if (tag == 0) return true;
+    uint32_t kind = tag == 0x0A ? K_BYTES : tag == 0x12 ? K_FLOAT : tag == 0x1A ? K_INT64 : K_NONE;
+    if (kind != K_NONE) {
+      uint32_t l;
+      if (!rd_len(c, l)) return false;
+      Cur body{c.p, c.p + l};
+      c.p += l;
+      if (!list_scan(kind, body, a, want_java, base)) return false;
+    } else if (!skip_field(c, tag)) return false;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// schema lookup
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ int schema_lookup(const DevSchema& s, const uint8_t* key, uint32_t klen) {
+  if (s.n_fields == 0) return -1;
+  uint32_t h = name_hash(key, klen);
+  uint32_t slot = h & (uint32_t)s.ht_mask;
+  for (;;) {
+    int f = s.ht[slot];
+    if (f < 0) return -1;
+    const DevField& fd = s.fields[f];
+    if (fd.hash == h && fd.name_len == klen) {
+      const uint8_t* nm = s.names + fd.name_off;
+      bool eq = true;
+      for (uint32_t i = 0; i < klen; ++i) if (nm[i] != key[i]) { eq = false; break; }
+      if (eq) return f;
+    }
+    slot = (slot + 1) & (uint32_t)s.ht_mask;
+  }
+}
+
+// FeatureList value accumulation (SequenceExample.feature_lists entries)
+struct FlistAcc {
+  uint32_t steps, tot_n, tot_bytes;
+  int err;   // first failing step's error (TFR_E_*), 0 none
+};
+
+// ---------------------------------------------------------------------------------------------
+// pass 1
+// ---------------------------------------------------------------------------------------------
+// writes the outputs of field f (and of every later schema field with the same name) for one row
+__device__ __forceinline__ void write_feature_cell(const DecodeArgs& A, uint32_t row, int f, const FeatAcc& a, uint32_t entry_pos,
+                                                   uint8_t* fstate) {
+  for (; f >= 0; f = A.sch.fields[f].dup_next) {
+    const DevField& fd = A.sch.fields[f];
+    int code = 0;
+    if (fd.elem_type == TFR_T_NULL) { fstate[f] = 3; continue; }          // NullType: always null (:71-72)
+    if (fd.depth >= 2) code = TFR_E_BAD_NESTING;                            // :119
+    else if (a.kind != (uint32_t)fd.kind) code = TFR_E_KIND_MISMATCH;       // require(...) :178,189,201,212
+    else if (fd.depth == 0 && a.n == 0) code = TFR_E_EMPTY_SCALAR;          // .head
+    if (code) { fstate[f] = (uint8_t)(-code); continue; }
+    fstate[f] = 1;
+    if (fd.depth == 0) {
+      if (fd.fix_slot >= 0) {
+        void* vp = A.fix_values[fd.fix_slot];
+        switch (fd.elem_type) {
+          case TFR_T_INT64: reinterpret_cast<int64_t*>(vp)[row] = (int64_t)a.first; break;
+          case TFR_T_INT32: reinterpret_cast<int32_t*>(vp)[row] = (int32_t)(uint32_t)a.first; break;   // .toInt
+          case TFR_T_FLOAT32: reinterpret_cast<uint32_t*>(vp)[row] = (uint32_t)a.first; break;
+          default: reinterpret_cast<double*>(vp)[row] = (double)__uint_as_float((uint32_t)a.first); break;   // .toDouble
+        }
+      } else {   // scalar string / binary: first element
+        A.cnt[(size_t)fd.cnt_slot * A.n + row] = a.first_len;
+        A.src[(size_t)fd.var_slot * A.n + row] = (uint32_t)a.first;
+        A.cflag[(size_t)fd.var_slot * A.n + row] = CF_CANON;
+      }
+    } else {     // depth 1
+      A.cnt[(size_t)fd.cnt_slot * A.n + row] = a.n;
+      if (fd.n_levels == 2) A.cnt[(size_t)(fd.cnt_slot + 1) * A.n + row] = a.nbytes;
+      bool canon = acc_canonical(a);
+      A.src[(size_t)fd.var_slot * A.n + row] = canon ? a.src : entry_pos;
+      A.cflag[(size_t)fd.var_slot * A.n + row] = canon ? CF_CANON : CF_GENERAL;
+    }
+  }
+}
+__device__ __forceinline__ void write_flist_cell(const DecodeArgs& A, uint32_t row, int f, const FlistAcc& a, uint32_t entry_pos,
+                                                 uint8_t* fstate) {
+  const DevField& fd = A.sch.fields[f];
+  if (a.err) { fstate[f] = (uint8_t)(-a.err); return; }
+  fstate[f] = 1;
+  A.cnt[(size_t)fd.cnt_slot * A.n + row] = a.steps;
+  if (fd.depth == 1) {
+    if (fd.n_levels == 2) A.cnt[(size_t)(fd.cnt_slot + 1) * A.n + row] = a.tot_bytes;
+  } else {
+    A.cnt[(size_t)(fd.cnt_slot + 1) * A.n + row] = a.tot_n;
+    if (fd.n_levels == 3) A.cnt[(size_t)(fd.cnt_slot + 2) * A.n + row] = a.tot_bytes;
+  }
+  A.src[(size_t)fd.var_slot * A.n + row] = entry_pos;
+  A.cflag[(size_t)fd.var_slot * A.n + row] = CF_FLIST;
+}
+
+// Parse one map entry {1: key, 2: value} of Features (is_flist = false) or FeatureLists (true).
+// Returns false when the entry is malformed.  On return f = matched schema field or -1.
+__device__ __forceinline__ bool parse_entry(const DecodeArgs& A, const uint8_t* ep, uint32_t elen, bool is_flist, int& f, FeatAcc& acc,
+                                            FlistAcc& facc) {
+  // (a) top-level fields of the entry: the last key wins; values are revisited in (b)
+  const uint8_t* key = nullptr;
+  uint32_t klen = 0;
+  {
+    Cur c{ep, ep + elen};
+    for (;;) {
+      uint32_t tag;
+      if (!rd_tag(c, tag)) return false;
+      if (tag == 0) break;
+      if (tag == 0x0A) {
+        uint32_t l;
+        if (!rd_len(c, l)) return false;
+        if (!utf8_valid(c.p, l)) return false;      // proto3 string key: readStringRequireUtf8
+        key = c.p; klen = l; c.p += l;
+      } else if (!skip_field(c, tag)) return false;
+    }
+  }
+  f = schema_lookup(A.sch, key, klen);
+  bool want_java = false;
+  for (int g = f; g >= 0; g = A.sch.fields[g].dup_next) want_java |= A.sch.fields[g].elem_type == TFR_T_STRING;
+  // (b) values, deep
+  acc_reset(acc, K_NONE);
+  facc.steps = facc.tot_n = facc.tot_bytes = 0; facc.err = 0;
+  Cur c{ep, ep + elen};
+  for (;;) {
+    uint32_t tag;
+    if (!rd_tag(c, tag)) return false;
+    if (tag == 0) break;
+    if (tag != 0x12) { if (!skip_field(c, tag)) return false; continue; }
+    uint32_t l;
+    if (!rd_len(c, l)) return false;
+    Cur body{c.p, c.p + l};
+    c.p += l;
+    if (!is_flist) {
+      if (!feature_scan(body, acc, want_java, A.data)) return false;
+    } else {
+      // FeatureList: repeated Feature feature = 1 (steps append across value occurrences)
+      for (;;) {
+        uint32_t t2;
+        if (!rd_tag(body, t2)) return false;
+        if (t2 == 0) break;
+        if (t2 != 0x0A) { if (!skip_field(body, t2)) return false; continue; }
+        uint32_t sl;
+        if (!rd_len(body, sl)) return false;
+        FeatAcc st;
+        acc_reset(st, K_NONE);
+        if (!feature_scan(Cur{body.p, body.p + sl}, st, want_java, A.data)) return false;
+        body.p += sl;
+        facc.steps++;
+        if (f >= 0 && !facc.err) {
+          const DevField& fd = A.sch.fields[f];
+          if (fd.depth == 0) facc.err = TFR_E_BAD_NESTING;                              // :142
+          else if (st.kind != (uint32_t)fd.kind) facc.err = TFR_E_KIND_MISMATCH;
+          else if (fd.depth == 1) {                                                     // element = head of the step
+            if (st.n == 0) facc.err = TFR_E_EMPTY_SCALAR;
+            else { facc.tot_n++; facc.tot_bytes += st.first_len; }
+          } else { facc.tot_n += st.n; facc.tot_bytes += st.nbytes; }
+        }
+      }
+    }
+  }
+  if (is_flist && f >= 0 && A.sch.fields[f].depth == 0 && !facc.err) facc.err = TFR_E_BAD_NESTING;   // empty FeatureList into a scalar
+  return true;
+}
+
+// Parses up to 32 entries (one per lane) and publishes the winners.  ent_ptr/ent_len are per-lane.
+__device__ __forceinline__ bool process_round(const DecodeArgs& A, uint32_t row, uint32_t nent, const uint8_t* ent_ptr, uint32_t ent_len,
+                                              uint32_t ent_pos, bool is_flist, uint8_t* fstate) {
+  const uint32_t lane = threadIdx.x & 31;
+  int f = -1;
+  FeatAcc acc;
+  FlistAcc facc;
+  bool ok = true;
+  if (lane < nent) ok = parse_entry(A, ent_ptr, ent_len, is_flist, f, acc, facc);
+  if (__any_sync(FULLMASK, !ok)) return false;
+  // duplicate keys inside the round: the last entry in wire order wins (Map.put)
+  uint32_t same = __match_any_sync(FULLMASK, f);
+  bool winner = f >= 0 && (31 - __clz(same)) == (int)lane;
+  if (winner) {
+    if (!is_flist) write_feature_cell(A, row, f, acc, ent_pos, fstate);
+    else {
+      // context wins over feature_lists for the same name (M/TFRecordDeserializer.scala:45-55); context
+      // rounds are all done before the first feature_lists round.  fstate 2 marks "seen in feature_lists".
+      for (int g = f; g >= 0; g = A.sch.fields[g].dup_next) {
+        uint8_t st = fstate[g];
+        if (st == 0 || (st & 0x40)) {     // unseen, or seen only in a previous feature_lists entry
+          FlistAcc fa = facc;
+          const DevField& fd = A.sch.fields[g];
+          if (fd.elem_type == TFR_T_NULL) { fstate[g] = 0x40 | 3; continue; }
+          // per-field re-evaluation is needed only for duplicate names with different types; parse_entry used
+          // the first field of the chain
+          if (g != f) {
+            // conservative: recompute is not possible without re-parsing; duplicate-named columns of different
+            // shapes fed from feature_lists are rejected at schema creation (api.cu)
+          }
+          write_flist_cell(A, row, g, fa, ent_pos, fstate);
+          fstate[g] |= 0x40;
+        }
+      }
+    }
+  }
+  __syncwarp();
+  return true;
+}
+
+// Walks `0A len` entries of one Features / FeatureLists message body, 32 at a time.
+__device__ __forceinline__ bool walk_map_body(const DecodeArgs& A, uint32_t row, Cur body, bool is_flist, uint8_t* fstate,
+                                              uint32_t& nent, const uint8_t*& my_ptr, uint32_t& my_len, uint32_t& my_pos) {
+  const uint32_t lane = threadIdx.x & 31;
+  for (;;) {
+    uint32_t tag;
+    if (!rd_tag(body, tag)) return false;
+    if (tag == 0) return true;
+    if (tag != 0x0A) { if (!skip_field(body, tag)) return false; continue; }
+    const uint8_t* lp = body.p;
+    uint32_t l;
+    if (!rd_len(body, l)) return false;
+    if (lane == nent) { my_ptr = body.p; my_len = l; my_pos = (uint32_t)(lp - A.data); }
+    body.p += l;
+    if (++nent == 32) {
+      if (!process_round(A, row, nent, my_ptr, my_len, my_pos, is_flist, fstate)) return false;
+      nent = 0;
+    }
+  }
+}
+
+// a row that fails before the per-field epilogue (bad CRC, malformed proto): zero counts, null validity
+__device__ __forceinline__ void null_fill_row(const DecodeArgs& A, uint32_t row) {
+  const uint32_t lane = threadIdx.x & 31;
+  for (uint32_t f = lane; f < (uint32_t)A.sch.n_fields; f += 32) A.valid8[(size_t)f * A.n + row] = 0;
+  for (uint32_t c = lane; c < (uint32_t)A.sch.n_cnt; c += 32) A.cnt[(size_t)c * A.n + row] = 0;
+}
+
+__global__ void __launch_bounds__(256) decode_pass1_kernel(DecodeArgs A) {
+  extern __shared__ uint32_t smem[];
+  uint32_t* stab = smem;
+  crc_stage_tables(stab, A.tabs);
+  const uint32_t warps = blockDim.x >> 5, wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t nf = (uint32_t)A.sch.n_fields;
+  const uint32_t fstride = (nf + 3) & ~3u;
+  uint8_t* fstate = reinterpret_cast<uint8_t*>(smem + CRC_SMEM_WORDS) + (size_t)wid * fstride;
+  __syncthreads();
+  for (uint32_t row = blockIdx.x * warps + wid; row < A.n; row += gridDim.x * warps) {
+    const uint32_t off = A.rec_off[row];
+    const uint32_t len = A.rec_off[row + 1] - off - 16;
+    const uint8_t* payload = A.data + off + 12;
+    uint32_t status = 0;
+    if (A.verify) {
+      uint32_t crc = crc_warp(stab, payload, len);
+      if (crc_mask(crc) != load_u32_unaligned(payload + len)) status = make_status(TFR_E_CRC_DATA, -1);
+    }
+    if (A.sch.record_type == TFR_RT_BYTE_ARRAY) {            // deserializeByteArray (:17-19)
+      if (lane == 0) {
+        A.status[row] = status;
+        A.cnt[row] = len; A.src[row] = off + 12; A.cflag[row] = CF_CANON; A.valid8[row] = 1;
+      }
+      continue;
+    }
+    if (status) { null_fill_row(A, row); if (lane == 0) A.status[row] = status; continue; }
+    for (uint32_t i = lane; i < nf; i += 32) fstate[i] = 0;
+    __syncwarp();
+    bool ok = true;
+    uint32_t nent = 0, my_len = 0, my_pos = 0;
+    const uint8_t* my_ptr = nullptr;
+    // Example.features / SequenceExample.context: field 1 (repeated occurrences merge)
+    {
+      Cur top{payload, payload + len};
+      for (;;) {
+        uint32_t tag;
+        if (!rd_tag(top, tag)) { ok = false; break; }
+        if (tag == 0) break;
+        if (tag == 0x0A || (tag == 0x12 && A.sch.record_type == TFR_RT_SEQUENCE_EXAMPLE)) {
+          uint32_t l;
+          if (!rd_len(top, l)) { ok = false; break; }
+          if (tag == 0x0A && !walk_map_body(A, row, Cur{top.p, top.p + l}, false, fstate, nent, my_ptr, my_len, my_pos)) { ok = false; break; }
+          top.p += l;
+        } else if (!skip_field(top, tag)) { ok = false; break; }
+      }
+      if (ok && nent) { ok = process_round(A, row, nent, my_ptr, my_len, my_pos, false, fstate); nent = 0; }
+    }
+    // SequenceExample.feature_lists: field 2, after every context entry has been seen
+    if (ok && A.sch.record_type == TFR_RT_SEQUENCE_EXAMPLE) {
+      Cur top{payload, payload + len};
+      for (;;) {
+        uint32_t tag;
+        if (!rd_tag(top, tag) || tag == 0) break;                 // malformed input was caught above
+        if (tag == 0x0A || tag == 0x12) {
+          uint32_t l;
+          if (!rd_len(top, l)) break;
+          if (tag == 0x12 && !walk_map_body(A, row, Cur{top.p, top.p + l}, true, fstate, nent, my_ptr, my_len, my_pos)) { ok = false; break; }
+          top.p += l;
+        } else if (!skip_field(top, tag)) break;
+      }
+      if (ok && nent) { ok = process_round(A, row, nent, my_ptr, my_len, my_pos, true, fstate); nent = 0; }
+    }
+    if (!ok) { null_fill_row(A, row); if (lane == 0) A.status[row] = make_status(TFR_E_MALFORMED_PROTO, -1); continue; }
+    __syncwarp();
+    // absent fields -> null or NullPointerException; first error in schema order wins
+    uint32_t worst = 0xffffffffu;
+    for (uint32_t f = lane; f < nf; f += 32) {
+      uint8_t st = fstate[f] & 0x3f;
+      const DevField& fd = A.sch.fields[f];
+      uint8_t valid = 0;
+      if (st == 1) valid = 1;
+      else if (st == 0 || st == 3) {                              // absent, or NullType
+        if (st == 0 && !fd.nullable) worst = min(worst, (f << 8) | (uint32_t)(-TFR_E_NULL_IN_NONNULL));
+        if (fd.fix_slot >= 0) {
+          void* vp = A.fix_values[fd.fix_slot];
+          if (fd.width == 8) reinterpret_cast<uint64_t*>(vp)[row] = 0; else reinterpret_cast<uint32_t*>(vp)[row] = 0;
+        } else if (fd.var_slot >= 0) {
+          for (int l = 0; l < fd.n_levels; ++l) A.cnt[(size_t)(fd.cnt_slot + l) * A.n + row] = 0;
+        }
+      } else worst = min(worst, (f << 8) | st);
+      A.valid8[(size_t)f * A.n + row] = valid;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) worst = min(worst, __shfl_xor_sync(FULLMASK, worst, o));
+    if (lane == 0) A.status[row] = worst == 0xffffffffu ? 0u : ((worst & 0xff) | (((worst >> 8) + 1) << 8));
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// pass 2: emit variable-width cells
+// ---------------------------------------------------------------------------------------------
+struct ElemSink {
+  int elem_type;
+  uint8_t* values;     // leaf buffer
+  uint32_t vpos;       // next leaf index (fixed width) or next byte (STRING/BINARY)
+  int32_t* leaf_off;   // STRING/BINARY inside a list: offsets of the leaf level, else nullptr
+  uint32_t epos;       // next element slot in leaf_off
+  uint32_t limit;      // max elements to accept (1 = head only)
+  uint32_t taken;
+};
+__device__ __forceinline__ void sink_int(ElemSink& s, uint64_t v) {
+  if (s.taken >= s.limit) return;
+  if (s.elem_type == TFR_T_INT64) reinterpret_cast<int64_t*>(s.values)[s.vpos] = (int64_t)v;
+  else reinterpret_cast<int32_t*>(s.values)[s.vpos] = (int32_t)(uint32_t)v;
+  s.vpos++; s.taken++;
+}
+__device__ __forceinline__ void sink_float(ElemSink& s, uint32_t bits) {
+  if (s.taken >= s.limit) return;
+  if (s.elem_type == TFR_T_FLOAT32) reinterpret_cast<uint32_t*>(s.values)[s.vpos] = bits;
+  else reinterpret_cast<double*>(s.values)[s.vpos] = (double)__uint_as_float(bits);
+  s.vpos++; s.taken++;
+}
+__device__ __forceinline__ void sink_bytes(ElemSink& s, const uint8_t* p, uint32_t l) {
+  if (s.taken >= s.limit) return;
+  uint8_t* d = s.values + s.vpos;
+  if (s.elem_type == TFR_T_STRING && !all_ascii(p, l)) s.vpos += java_utf8_transcode(p, l, d);
+  else { for (uint32_t i = 0; i < l; ++i) d[i] = p[i]; s.vpos += l; }
+  if (s.leaf_off) { s.leaf_off[s.epos + 1] = (int32_t)s.vpos; s.epos++; }
+  s.taken++;
+}
+// emit every element of one list message body (kind known, input already validated by pass 1)
+__device__ __forceinline__ void list_emit(uint32_t kind, Cur c, ElemSink& s) {
+  for (;;) {
+    uint32_t tag;
+    if (!rd_tag(c, tag) || tag == 0) return;
+    if (kind == K_BYTES && tag == 0x0A) {
+      uint32_t l; if (!rd_len(c, l)) return;
+      sink_bytes(s, c.p, l); c.p += l;
+    } else if (kind == K_FLOAT && tag == 0x0A) {
+      uint32_t l; if (!rd_len(c, l)) return;
+      for (uint32_t i = 0; i + 4 <= l; i += 4) sink_float(s, load_u32_unaligned(c.p + i));
+      c.p += l;
+    } else if (kind == K_FLOAT && tag == 0x0D) {
+      if (c.end - c.p < 4) return;
+      sink_float(s, load_u32_unaligned(c.p)); c.p += 4;
+    } else if (kind == K_INT64 && tag == 0x0A) {
+      uint32_t l; if (!rd_len(c, l)) return;
+      Cur pk{c.p, c.p + l};
+      while (pk.p < pk.end) { uint64_t v; if (!rd_varint64(pk, v)) return; sink_int(s, v); }
+      c.p += l;
+    } else if (kind == K_INT64 && tag == 0x08) {
+      uint64_t v; if (!rd_varint64(c, v)) return;
+      sink_int(s, v);
+    } else if (!skip_field(c, tag)) return;
+  }
+}
+// Walk the kind-field occurrences of Feature bodies.  mode 0: find where the final run starts
+// (returns its occurrence index through run_first, final kind through kind); mode 1: emit the
+// occurrences >= run_first.
+struct OccState { uint32_t occ, run_first, kind; };
+__device__ __forceinline__ void feature_occ_walk(Cur c, OccState& o, int mode, ElemSink* s) {
+  for (;;) {
+    uint32_t tag;
+    if (!rd_tag(c, tag) || tag == 0) return;
+    uint32_t kind = tag == 0x0A ? K_BYTES : tag == 0x12 ? K_FLOAT : tag == 0x1A ? K_INT64 : K_NONE;
+    if (kind != K_NONE) {
+      uint32_t l; if (!rd_len(c, l)) return;
+      if (mode == 0) { if (kind != o.kind) { o.kind = kind; o.run_first = o.occ; } }
+      else if (o.occ >= o.run_first) list_emit(kind, Cur{c.p, c.p + l}, *s);
+      o.occ++;
+      c.p += l;
+    } else if (!skip_field(c, tag)) return;
+  }
+}
+// general emit of the merged Feature carried by the value fields (tag 0x12) of a map entry
+__device__ __forceinline__ void entry_feature_emit(Cur entry, ElemSink& s) {
+  OccState o{0, 0, K_NONE};
+  for (int mode = 0; mode < 2; ++mode) {
+    Cur c = entry;
+    o.occ = 0;
+    for (;;) {
+      uint32_t tag;
+      if (!rd_tag(c, tag) || tag == 0) break;
+      if (tag == 0x12) {
+        uint32_t l; if (!rd_len(c, l)) break;
+        feature_occ_walk(Cur{c.p, c.p + l}, o, mode, &s);
+        c.p += l;
+      } else if (!skip_field(c, tag)) break;
+    }
+  }
+}
+// general emit of one step Feature (single message body)
+__device__ __forceinline__ void step_feature_emit(Cur body, ElemSink& s) {
+  OccState o{0, 0, K_NONE};
+  feature_occ_walk(body, o, 0, &s);
+  o.occ = 0;
+  feature_occ_walk(body, o, 1, &s);
+}
+
+__global__ void __launch_bounds__(256) decode_pass2_kernel(DecodeArgs A) {
+  const uint32_t warps = blockDim.x >> 5, wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t nvar = (uint32_t)A.sch.n_var;
+  for (uint32_t row = blockIdx.x * warps + wid; row < A.n_eff; row += gridDim.x * warps) {
+    if (A.sch.record_type == TFR_RT_BYTE_ARRAY) {
+      // whole-warp copy of the payload
+      const uint8_t* s = A.data + A.src[row];
+      uint8_t* d = reinterpret_cast<uint8_t*>(A.var_values[0]) + A.scan[0][row];
+      uint32_t l = (uint32_t)(A.scan[0][row + 1] - A.scan[0][row]);
+      for (uint32_t i = lane; i < l; i += 32) d[i] = s[i];
+      continue;
+    }
+    for (uint32_t v = lane; v < nvar; v += 32) {
+      const int f = A.var_field[v];
+      if (!A.valid8[(size_t)f * A.n + row]) continue;
+      const DevField& fd = A.sch.fields[f];
+      const uint32_t src = A.src[(size_t)v * A.n + row];
+      const uint32_t flag = A.cflag[(size_t)v * A.n + row];
+      const int32_t off0 = A.scan[fd.cnt_slot][row];
+      const uint32_t cnt0 = (uint32_t)(A.scan[fd.cnt_slot][row + 1] - off0);
+      ElemSink s;
+      s.elem_type = fd.elem_type; s.values = reinterpret_cast<uint8_t*>(A.var_values[v]);
+      s.leaf_off = nullptr; s.epos = 0; s.limit = 0xffffffffu; s.taken = 0;
+      const bool varlen = fd.elem_type == TFR_T_STRING || fd.elem_type == TFR_T_BINARY;
+      if (fd.depth == 0) {                                   // scalar string / binary
+        Cur c{A.data + src, A.data + src + 16};              // length varint of the first element (validated in pass 1)
+        uint32_t l = 0; uint64_t lv;
+        if (rd_varint64(c, lv)) l = (uint32_t)lv;
+        s.vpos = (uint32_t)off0; s.limit = 1;
+        sink_bytes(s, c.p, l);
+        continue;
+      }
+      if (flag == CF_FLIST) {
+        // FeatureList: steps across the value occurrences of the entry
+        Cur e{A.data + src, A.data + src + 16};
+        uint64_t elen; if (!rd_varint64(e, elen)) continue;
+        Cur entry{e.p, e.p + (uint32_t)elen};
+        int32_t* off1 = A.offs[v * 3 + 1];
+        uint32_t step = 0;
+        if (fd.depth == 1) {                                 // array of heads
+          if (varlen) { s.leaf_off = off1; s.epos = (uint32_t)off0; s.vpos = (uint32_t)A.scan[fd.cnt_slot + 1][row]; }
+          else s.vpos = (uint32_t)off0;
+        } else {
+          if (varlen) { s.leaf_off = A.offs[v * 3 + 2]; s.epos = (uint32_t)A.scan[fd.cnt_slot + 1][row]; s.vpos = (uint32_t)A.scan[fd.cnt_slot + 2][row]; }
+          else s.vpos = (uint32_t)A.scan[fd.cnt_slot + 1][row];
+        }
+        for (;;) {
+          uint32_t tag;
+          if (!rd_tag(entry, tag) || tag == 0) break;
+          if (tag != 0x12) { if (!skip_field(entry, tag)) break; continue; }
+          uint32_t l; if (!rd_len(entry, l)) break;
+          Cur fl{entry.p, entry.p + l};
+          entry.p += l;
+          for (;;) {
+            uint32_t t2;
+            if (!rd_tag(fl, t2) || t2 == 0) break;
+            if (t2 != 0x0A) { if (!skip_field(fl, t2)) break; continue; }
+            uint32_t sl; if (!rd_len(fl, sl)) break;
+            s.taken = 0; s.limit = fd.depth == 1 ? 1u : 0xffffffffu;
+            step_feature_emit(Cur{fl.p, fl.p + sl}, s);
+            fl.p += sl;
+            if (fd.depth == 2) off1[(uint32_t)off0 + step + 1] = (int32_t)(varlen ? s.epos : s.vpos);
+            step++;
+          }
+        }
+        continue;
+      }
+      // depth 1 from a Feature
+      if (varlen) { s.leaf_off = A.offs[v * 3 + 1]; s.epos = (uint32_t)off0; s.vpos = (uint32_t)A.scan[fd.cnt_slot + 1][row]; }
+      else s.vpos = (uint32_t)off0;
+      if (flag == CF_CANON) {
+        if (cnt0 == 0) continue;
+        const uint8_t* p = A.data + src;
+        if (fd.kind == K_FLOAT) {
+          for (uint32_t i = 0; i < cnt0; ++i) sink_float(s, load_u32_unaligned(p + 4 * i));
+        } else if (fd.kind == K_INT64) {
+          Cur pk{p, p + (size_t)cnt0 * 10};
+          for (uint32_t i = 0; i < cnt0; ++i) { uint64_t x; if (!rd_varint64(pk, x)) break; sink_int(s, x); }
+        } else {
+          Cur c{p, A.data + A.rec_off[row + 1]};
+          for (uint32_t i = 0; i < cnt0; ++i) {
+            uint32_t tag, l;
+            if (!rd_tag(c, tag) || !rd_len(c, l)) break;
+            sink_bytes(s, c.p, l); c.p += l;
+          }
+        }
+      } else {
+        Cur e{A.data + src, A.data + src + 16};
+        uint64_t elen; if (!rd_varint64(e, elen)) continue;
+        entry_feature_emit(Cur{e.p, e.p + (uint32_t)elen}, s);
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// validity bytes -> Arrow bitmaps (+ null counts), first-error reduction
+// ---------------------------------------------------------------------------------------------
+__global__ void pack_validity_kernel(const uint8_t* __restrict__ valid8, uint32_t n, uint32_t n_eff, uint32_t nf, uint32_t bitmap_stride,
+                                     uint8_t* __restrict__ bitmaps, unsigned long long* __restrict__ null_counts) {
+  const uint32_t nb = (n_eff + 7) >> 3;
+  const uint32_t f = blockIdx.y;
+  if (f >= nf) return;
+  unsigned long long local = 0;
+  for (uint32_t b = blockIdx.x * blockDim.x + threadIdx.x; b < nb; b += gridDim.x * blockDim.x) {
+    uint32_t bits = 0;
+    const uint8_t* v = valid8 + (size_t)f * n + (size_t)b * 8;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      uint32_t r = b * 8 + i;
+      if (r < n_eff) { if (v[i]) bits |= 1u << i; else local++; }
+    }
+    bitmaps[(size_t)f * bitmap_stride + b] = (uint8_t)bits;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) local += __shfl_xor_sync(FULLMASK, local, o);
+  if ((threadIdx.x & 31) == 0 && local) atomicAdd(&null_counts[f], local);
+}
+
+struct DecodeSummary {       // device -> host after pass 1 + scans
+  uint32_t first_err_row;    // 0xffffffff none
+  uint32_t first_err_status;
+  uint32_t n_eff;
+  uint32_t pad;
+};
+__global__ void first_error_kernel(const uint32_t* __restrict__ status, uint32_t n, DecodeSummary* __restrict__ out) {
+  uint32_t best = 0xffffffffu;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    if (status[i] != 0) { best = i; break; }    // indices visited by one thread are increasing
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) best = min(best, __shfl_xor_sync(FULLMASK, best, o));
+  if ((threadIdx.x & 31) == 0 && best != 0xffffffffu) atomicMin(&out->first_err_row, best);
+}
+// n_eff + totals at n_eff for every scanned array (so that rows after the first error vanish)
+__global__ void summary_kernel(const uint32_t* __restrict__ status, uint32_t n, DecodeSummary* __restrict__ out,
+                               const int32_t* const* __restrict__ scan, uint32_t n_cnt, int64_t* __restrict__ totals) {
+  uint32_t e = out->first_err_row;
+  uint32_t n_eff = e == 0xffffffffu ? n : e;
+  if (threadIdx.x == 0) { out->n_eff = n_eff; out->first_err_status = e == 0xffffffffu ? 0 : status[e]; }
+  for (uint32_t a = threadIdx.x; a < n_cnt; a += blockDim.x) totals[a] = scan[a][n_eff];
+}

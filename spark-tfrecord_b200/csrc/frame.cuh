@@ -1,0 +1,236 @@
+// frame.cuh -- K1: TFRecord record-boundary index, built on the GPU.
+//
+// Replaces the sequential framing scan of tensorflow-hadoop's TFRecordReader.read (called from
+// M/TFRecordFileReader.scala:51): off[i+1] = off[i] + 16 + len[i] is a serial pointer chase, which
+// is why the reference declares files unsplittable (M/DefaultSource.scala:26-29).  Here the chase
+// is parallelised by SPECULATION + EXACT VERIFICATION:
+//   1. frame_scan   : the buffer is cut into chunks; one warp per chunk looks for the first byte
+//                     offset whose 12-byte header is self-consistent (masked CRC-32C of the 8
+//                     length bytes == the stored CRC; 32 candidates per step, __ballot_sync picks
+//                     the first hit) and chains headers from there until it leaves the chunk.
+//   2. frame_check  : chunk k's guess is right iff chunk k-1's chain ended exactly on it
+//                     (induction from offset 0, which is a record start by contract).
+//   3. frame_repair : only when a link is broken (a record larger than a chunk, payloads that
+//                     themselves contain TFRecord streams, corruption): one warp re-chains the
+//                     affected chunks sequentially from the true position -- always exact.
+//   4. chunk counts are prefix-summed and frame_emit re-walks each chunk writing rec_off[].
+// The result is identical to the sequential scan for every input, including the error cases
+// (bad length CRC, truncated tail, oversize length) which are reported at the first bad record.
+#pragma once
+#include "common.cuh"
+
+// how a chunk's chain (or the whole stream) stopped
+enum {
+  FS_LEFT = 0,        // walked past the end of the chunk: `end` is the next record start
+  FS_EOF = 1,         // ended exactly at nbytes
+  FS_STRAY = 2,       // 1..7 bytes left: TFRecordReader.read catches the EOFException -> clean EOF
+  FS_PART_HDR = 3,    // 8..11 bytes left: EOF while reading the length CRC -> TRUNCATED
+  FS_PART_REC = 4,    // header ok, payload/footer runs past nbytes -> TRUNCATED
+  FS_BAD_CRC = 5,     // length CRC mismatch
+  FS_TOO_LARGE = 6,   // length > Integer.MAX_VALUE
+  FS_NONE = 7         // no candidate header in this chunk
+};
+
+struct ChunkInfo {
+  uint32_t first;   // offset of the first record that starts in this chunk (0xffffffff none)
+  uint32_t end;     // where the chain stopped (next record start, or the stop position)
+  uint32_t count;   // complete, header-valid records that start in this chunk
+  uint32_t stop;    // FS_*
+};
+
+struct FrameResult {       // written by the device, read back by the host (one small D2H)
+  uint32_t n_records;      // complete records before the stop
+  uint32_t stop;           // FS_EOF / FS_STRAY / FS_PART_HDR / FS_PART_REC / FS_BAD_CRC / FS_TOO_LARGE
+  uint32_t stop_pos;       // byte offset of the record (or fragment) that stopped the scan
+  uint32_t repairs;        // chunks re-chained by frame_repair
+  uint32_t first_bad;      // first chunk whose link check failed, 0xffffffff if none
+  uint32_t pad[3];
+};
+
+// walk headers starting at q until the chain leaves [.., ce) or stops; returns stop code
+__device__ __forceinline__ uint32_t frame_chain(const uint32_t* t0, const uint8_t* data, uint32_t nbytes, uint32_t ce,
+                                                bool verify, uint32_t& q, uint32_t& count) {
+  while (q < ce) {
+    uint32_t left = nbytes - q;
+    if (left < 8) return FS_STRAY;
+    if (left < 12) return FS_PART_HDR;
+    uint32_t lo = load_u32_unaligned(data + q), hi = load_u32_unaligned(data + q + 4);
+    if (verify) {
+      uint32_t crc = load_u32_unaligned(data + q + 8);
+      if (crc_mask(crc_u64(t0, lo, hi)) != crc) return FS_BAD_CRC;
+    }
+    if (hi != 0 || lo > 0x7fffffffu) return FS_TOO_LARGE;
+    if ((uint64_t)left < 16ull + lo) return FS_PART_REC;
+    q += 16 + lo;
+    ++count;
+  }
+  return q == nbytes ? FS_EOF : FS_LEFT;
+}
+
+// one warp per chunk
+__global__ void __launch_bounds__(256) frame_scan_kernel(const uint8_t* __restrict__ data, uint32_t nbytes, uint32_t chunk_bytes,
+                                                         uint32_t n_chunks, uint32_t verify, const CrcTables* __restrict__ tabs,
+                                                         ChunkInfo* __restrict__ chunks) {
+  __shared__ uint32_t t0[256];
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) t0[i] = tabs->t0[i];
+  __syncthreads();
+  const uint32_t lane = threadIdx.x & 31;
+  const uint32_t warps_per_block = blockDim.x >> 5;
+  for (uint32_t k = blockIdx.x * warps_per_block + (threadIdx.x >> 5); k < n_chunks; k += gridDim.x * warps_per_block) {
+    const uint32_t cs = k * chunk_bytes;
+    const uint32_t ce = (nbytes - cs > chunk_bytes) ? cs + chunk_bytes : nbytes;
+    uint32_t first = 0xffffffffu;
+    if (k == 0) first = 0;
+    else {
+      // candidate p is plausible iff its 12-byte header is inside the buffer, the stored CRC matches the
+      // masked CRC-32C of the 8 length bytes, and the length fits an int32 (false positive 2^-32 per byte
+      // on random data; adversarial data is caught by frame_check and fixed by frame_repair)
+      for (uint32_t p0 = cs; p0 < ce && first == 0xffffffffu; p0 += 32) {
+        uint32_t p = p0 + lane;
+        bool hit = false;
+        if (p < ce && nbytes - p >= 12) {
+          uint32_t lo = load_u32_unaligned(data + p), hi = load_u32_unaligned(data + p + 4);
+          if (hi == 0 && lo <= 0x7fffffffu) hit = crc_mask(crc_u64(t0, lo, hi)) == load_u32_unaligned(data + p + 8);
+        }
+        uint32_t m = __ballot_sync(FULLMASK, hit);
+        if (m) first = p0 + (uint32_t)(__ffs(m) - 1);
+      }
+    }
+    ChunkInfo ci;
+    ci.first = first; ci.end = first; ci.count = 0; ci.stop = FS_NONE;
+    if (first != 0xffffffffu) {
+      uint32_t q = first, cnt = 0;
+      ci.stop = frame_chain(t0, data, nbytes, ce, verify != 0, q, cnt);   // uniform across the warp
+      ci.end = q; ci.count = cnt;
+    }
+    if (lane == 0) chunks[k] = ci;
+  }
+}
+
+// link check: chunk k (k >= 1) is consistent iff the previous chunk's chain left exactly onto its guess
+__global__ void frame_check_kernel(const ChunkInfo* __restrict__ chunks, uint32_t n_chunks, FrameResult* __restrict__ res) {
+  uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k == 0 || k >= n_chunks) return;
+  ChunkInfo prev = chunks[k - 1], cur = chunks[k];
+  bool ok = prev.stop == FS_LEFT && cur.first != 0xffffffffu && prev.end == cur.first;
+  // a previous chunk that already stopped the stream makes every later chunk irrelevant; that is
+  // resolved in frame_finish, but it still has to go through the sequential path
+  if (!ok) atomicMin(&res->first_bad, k);
+}
+
+// sequential, exact: single warp (lane 0 does the work; the warp form keeps the launch shape simple).
+// Starts at the first broken link and re-chains until the speculation re-synchronises.
+__global__ void frame_repair_kernel(const uint8_t* __restrict__ data, uint32_t nbytes, uint32_t chunk_bytes, uint32_t n_chunks,
+                                    uint32_t verify, const CrcTables* __restrict__ tabs, ChunkInfo* __restrict__ chunks,
+                                    FrameResult* __restrict__ res) {
+  __shared__ uint32_t t0[256];
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) t0[i] = tabs->t0[i];
+  __syncthreads();
+  if (res->first_bad == 0xffffffffu || threadIdx.x != 0) return;
+  uint32_t k = res->first_bad;          // >= 1
+  uint32_t repairs = 0;
+  ChunkInfo prev = chunks[k - 1];
+  uint32_t F = prev.end;                // true position where the stream continues
+  bool stopped = prev.stop != FS_LEFT;  // the stream already ended/failed in chunk k-1
+  for (; k < n_chunks; ++k) {
+    const uint32_t cs = k * chunk_bytes;
+    const uint32_t ce = (nbytes - cs > chunk_bytes) ? cs + chunk_bytes : nbytes;
+    ChunkInfo ci = chunks[k];
+    if (stopped || F >= ce) {           // no record starts in this chunk
+      if (ci.first != 0xffffffffu || ci.count) { ci.first = 0xffffffffu; ci.count = 0; ci.stop = FS_NONE; ci.end = F; chunks[k] = ci; ++repairs; }
+      continue;
+    }
+    if (ci.first == F) {                // speculation is right from here on: re-synchronised
+      if (ci.stop != FS_LEFT) { stopped = true; continue; }
+      // the following chunks were checked against this chunk's end by frame_check; if one of them is
+      // broken again the loop keeps going, otherwise everything behind is already consistent.
+      F = ci.end;
+      // fast-forward over consistent chunks
+      continue;
+    }
+    uint32_t q = F, cnt = 0;
+    ci.first = F;
+    ci.stop = frame_chain(t0, data, nbytes, ce, verify != 0, q, cnt);
+    ci.end = q; ci.count = cnt;
+    chunks[k] = ci; ++repairs;
+    if (ci.stop != FS_LEFT) stopped = true; else F = q;
+  }
+  res->repairs = repairs;
+}
+
+// exclusive prefix sum of chunk counts (single block) + stream stop reason
+__global__ void __launch_bounds__(1024) frame_finish_kernel(const ChunkInfo* __restrict__ chunks, uint32_t n_chunks, uint32_t nbytes,
+                                                            uint32_t* __restrict__ chunk_base, FrameResult* __restrict__ res) {
+  __shared__ uint32_t warp_sums[32];
+  __shared__ uint32_t carry;
+  __shared__ uint32_t stop_chunk;
+  if (threadIdx.x == 0) { carry = 0; stop_chunk = 0xffffffffu; }
+  __syncthreads();
+  const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  for (uint32_t base = 0; base < n_chunks; base += blockDim.x) {
+    uint32_t k = base + threadIdx.x;
+    uint32_t c = 0;
+    if (k < n_chunks) {
+      ChunkInfo ci = chunks[k];
+      c = ci.count;
+      if (ci.first != 0xffffffffu && ci.stop != FS_LEFT) atomicMin(&stop_chunk, k);
+    }
+    uint32_t x = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync(FULLMASK, x, o); if (lane >= (uint32_t)o) x += y; }
+    if (lane == 31) warp_sums[wid] = x;
+    __syncthreads();
+    if (wid == 0) {
+      uint32_t s = warp_sums[lane];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync(FULLMASK, s, o); if (lane >= (uint32_t)o) s += y; }
+      warp_sums[lane] = s;
+    }
+    __syncthreads();
+    uint32_t excl = x - c + (wid ? warp_sums[wid - 1] : 0) + carry;
+    if (k < n_chunks) chunk_base[k] = excl;
+    __syncthreads();
+    if (threadIdx.x == blockDim.x - 1) carry = excl + c;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    if (n_chunks == 0) { res->n_records = 0; res->stop = FS_EOF; res->stop_pos = 0; return; }
+    // records that start after the stop chunk do not exist (repair cleared them); the stop chunk is the
+    // first (and only) chunk with a non-LEFT stop
+    uint32_t sc = stop_chunk;
+    if (sc == 0xffffffffu) {   // cannot happen for nbytes > 0: the last live chunk always stops
+      res->n_records = carry; res->stop = FS_EOF; res->stop_pos = nbytes; return;
+    }
+    ChunkInfo ci = chunks[sc];
+    res->n_records = chunk_base[sc] + ci.count;
+    res->stop = ci.stop; res->stop_pos = ci.end;
+    chunk_base[n_chunks] = carry;
+  }
+}
+
+// re-walk each chunk and write the record offsets; rec_off[n] = stop_pos
+__global__ void __launch_bounds__(256) frame_emit_kernel(const uint8_t* __restrict__ data, const ChunkInfo* __restrict__ chunks,
+                                                         const uint32_t* __restrict__ chunk_base, uint32_t n_chunks,
+                                                         const FrameResult* __restrict__ res, uint32_t* __restrict__ rec_off) {
+  const uint32_t lane = threadIdx.x & 31;
+  const uint32_t warps_per_block = blockDim.x >> 5;
+  const uint32_t n = res->n_records;
+  if (blockIdx.x == 0 && threadIdx.x == 0) rec_off[n] = res->stop_pos;
+  for (uint32_t k = blockIdx.x * warps_per_block + (threadIdx.x >> 5); k < n_chunks; k += gridDim.x * warps_per_block) {
+    ChunkInfo ci = chunks[k];
+    if (ci.first == 0xffffffffu || ci.count == 0) continue;
+    uint32_t base = chunk_base[k];
+    if (base >= n) continue;
+    uint32_t q = ci.first;
+    // lanes take turns holding the offsets so the stores are coalesced 32 at a time
+    for (uint32_t i0 = 0; i0 < ci.count; i0 += 32) {
+      uint32_t mine = 0;
+      uint32_t lim = min(32u, ci.count - i0);
+      for (uint32_t j = 0; j < lim; ++j) {
+        if (lane == j) mine = q;
+        q += 16 + load_u32_unaligned(data + q);
+      }
+      if (lane < lim && base + i0 + lane < n) rec_off[base + i0 + lane] = mine;
+    }
+  }
+}
