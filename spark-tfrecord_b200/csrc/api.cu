@@ -246,6 +246,7 @@ struct HostStats {      // pinned, written by D2H copies
 };
 
 struct tfr_decoder {
+  std::atomic<int> refs{1};            // the creator + every live batch (exported Arrow arrays keep batches alive)
   tfr_schema schema;
   int device = 0;
   uint32_t flags = 0;
@@ -298,8 +299,10 @@ extern "C" int32_t tfr_decoder_create(const tfr_schema* schema, int32_t device, 
   *out = d;
   return TFR_OK;
 }
-extern "C" void tfr_decoder_destroy(tfr_decoder* d) {
-  if (!d) return;
+static void decoder_unref(tfr_decoder* d);
+extern "C" void tfr_decoder_destroy(tfr_decoder* d) { if (d) decoder_unref(d); }
+static void decoder_unref(tfr_decoder* d) {
+  if (d->refs.fetch_sub(1) != 1) return;
   cudaSetDevice(d->device);
   cudaStreamSynchronize(d->stream);
   for (DevBuf* b : {&d->in, &d->chunks, &d->chunk_base, &d->rec_off, &d->status, &d->valid8, &d->cnt, &d->src, &d->cflag, &d->tsum,
@@ -358,6 +361,7 @@ extern "C" int32_t tfr_decode(tfr_decoder* d, const void* data, size_t nbytes, i
   const uint32_t verify = (d->flags & TFR_F_VERIFY_CRC) ? 1u : 0u;
   auto* b = new tfr_batch;
   b->dec = d;
+  d->refs.fetch_add(1);
   b->info.error_row = -1; b->info.error_field = -1;
   std::unique_ptr<tfr_batch, void (*)(tfr_batch*)> guard(b, [](tfr_batch* x) { tfr_batch_release(x); });
 
@@ -487,7 +491,7 @@ extern "C" int32_t tfr_decode(tfr_decoder* d, const void* data, size_t nbytes, i
       scan_tile_bases_kernel<<<S.n_cnt, 1024, 0, st>>>(tsum, n_tiles, traw, d_overflow);
       scan_apply_kernel<<<dim3(n_tiles, S.n_cnt), SCAN_THREADS, 0, st>>>(A.cnt, n, n_tiles, tsum, traw, (int32_t* const*)dt_scan);
     }
-    summary_kernel<<<1, 256, 0, st>>>(A.status, n, d_sum, (const int32_t* const*)dt_scan, (uint32_t)S.n_cnt, d_totals);
+    summary_kernel<<<1, 256, 0, st>>>(A.status, A.rec_off, n, d_sum, (const int32_t* const*)dt_scan, (uint32_t)S.n_cnt, d_totals);
     CUDA_TRY(cudaMemcpyAsync(&d->h_stats->summary, d_sum, sizeof(DecodeSummary), cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaMemcpyAsync(&d->h_stats->overflow, d_overflow, 4, cudaMemcpyDeviceToHost, st));
     if (S.n_cnt) CUDA_TRY(cudaMemcpyAsync(totals, d_totals, (size_t)S.n_cnt * 8, cudaMemcpyDeviceToHost, st));
@@ -495,6 +499,11 @@ extern "C" int32_t tfr_decode(tfr_decoder* d, const void* data, size_t nbytes, i
     CUDA_TRY(cudaGetLastError());
     sum = d->h_stats->summary;
     n_eff = sum.n_eff;
+    if (sum.first_err_row != 0xffffffffu) {         // a failing record: the stream stops in front of it
+      used = sum.consumed;
+      if (consumed) *consumed = used;
+      b->info.consumed_bytes = (int64_t)used;
+    }
     if (d->h_stats->overflow) {
       // a prefix beyond int32 somewhere in the batch: only fatal if it is inside the delivered rows
       for (int a = 0; a < S.n_cnt; ++a) if (totals[a] < 0 || totals[a] > 0x7fffffffLL) return fail(TFR_E_BATCH_TOO_LARGE, "Arrow int32 offsets overflow; decode smaller blocks");
@@ -657,6 +666,7 @@ extern "C" void tfr_batch_release(tfr_batch* b) {
   if (b->host_copy) d->host_pool.give_back(b->host_copy);
   if (b->done) cudaEventDestroy(b->done);
   delete b;
+  decoder_unref(d);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -677,7 +677,7 @@ struct DecodeSummary {       // device -> host after pass 1 + scans
   uint32_t first_err_row;    // 0xffffffff none
   uint32_t first_err_status;
   uint32_t n_eff;
-  uint32_t pad;
+  uint32_t consumed;         // rec_off[n_eff]: bytes of the delivered rows
 };
 __global__ void first_error_kernel(const uint32_t* __restrict__ status, uint32_t n, DecodeSummary* __restrict__ out) {
   uint32_t best = 0xffffffffu;
@@ -688,10 +688,11 @@ __global__ void first_error_kernel(const uint32_t* __restrict__ status, uint32_t
   if ((threadIdx.x & 31) == 0 && best != 0xffffffffu) atomicMin(&out->first_err_row, best);
 }
 // n_eff + totals at n_eff for every scanned array (so that rows after the first error vanish)
-__global__ void summary_kernel(const uint32_t* __restrict__ status, uint32_t n, DecodeSummary* __restrict__ out,
-                               const int32_t* const* __restrict__ scan, uint32_t n_cnt, int64_t* __restrict__ totals) {
+__global__ void summary_kernel(const uint32_t* __restrict__ status, const uint32_t* __restrict__ rec_off, uint32_t n,
+                               DecodeSummary* __restrict__ out, const int32_t* const* __restrict__ scan, uint32_t n_cnt,
+                               int64_t* __restrict__ totals) {
   uint32_t e = out->first_err_row;
   uint32_t n_eff = e == 0xffffffffu ? n : e;
-  if (threadIdx.x == 0) { out->n_eff = n_eff; out->first_err_status = e == 0xffffffffu ? 0 : status[e]; }
+  if (threadIdx.x == 0) { out->n_eff = n_eff; out->first_err_status = e == 0xffffffffu ? 0 : status[e]; out->consumed = rec_off[n_eff]; }
   for (uint32_t a = threadIdx.x; a < n_cnt; a += blockDim.x) totals[a] = scan[a][n_eff];
 }
