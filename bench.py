@@ -1,0 +1,410 @@
+#!/usr/bin/env python
+"""bench.py -- TFRecord decode GB/s on BASELINE.json's configs[1] workload.
+
+    python bench.py --gpus N --steps K --warmup W            # our arm (one process per GPU under torchrun)
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path on the host cores
+
+A "step" is one pass of the hot path over one batch of synthetic framed TFRecord bytes
+(Example, 32 x Int64List[1] + 16 x FloatList[8] + 16 x BytesList[1] of 16 B, entries in schema order,
+CRC verified).  Prints ONE JSON line (rank 0).
+
+  value  : framed input GB/s with the batches already resident in HBM (CUDA events on the decoder's
+           stream around exactly K steps, max over ranks).
+  e2e    : the same metric through the C ABI with HOST buffers: every step copies the batch from pinned
+           host memory to the device, decodes, and copies all Arrow buffers back to pinned host memory
+           (what a row-based Spark consumer needs); 3 decoder handles keep H2D / kernels / D2H overlapped.
+  roofline: decode_pass1_kernel (the dominant kernel): algorithmic bytes per launch / its mean launch time
+           (CUDA events recorded by the library around every launch in the timed region), against the
+           measured HBM copy bandwidth in MEASURED_PEAKS.json.
+  cpu_baseline: the oracle port (C restatement of the reference's per-record algorithm) on the host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+METRIC = "TFRecord decode GB/s (1 KB Example, 64 mixed features) at 1/2/4/8 B200"
+UNIT = "GB/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=16)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch-mib", type=int, default=512, help="framed bytes per step (approx.)")
+    ap.add_argument("--pool", type=int, default=2, help="distinct batches cycled through")
+    ap.add_argument("--cpu-sample-mib", type=int, default=48, help="framed bytes each host thread decodes per pass")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    return ap.parse_args()
+
+
+def dist_env():
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    return rank, world, local
+
+
+# ---------------------------------------------------------------------------------------------
+# corpus: configs[1] records, encoded by the CPU oracle's writer (independent of the CUDA encoder)
+# ---------------------------------------------------------------------------------------------
+def make_batches(batch_mib: int, pool: int, seed: int):
+    from oracle import corpus, oracle
+    rec_bytes = 1728                      # measured mean framed record size of this schema (printed below)
+    n = max(1, (batch_mib << 20) // rec_bytes)
+    schema = corpus.cfg2_schema()
+    out = []
+    for i in range(pool):
+        _, cols = corpus.cfg2_columns(n, seed=seed + 1000 * i)
+        data, rc, _ = oracle.encode(cols, schema)
+        assert rc == 0
+        out.append(np.frombuffer(data, dtype=np.uint8))
+    return schema, n, out
+
+
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+# ---------------------------------------------------------------------------------------------
+# CPU arm: the oracle port on all host cores
+# ---------------------------------------------------------------------------------------------
+def record_aligned_slices(batch: np.ndarray, n_slices: int, slice_bytes: int):
+    """[(start, end)] of record-aligned windows spread over the batch"""
+    import struct
+    offs = [0]
+    pos = 0
+    n = len(batch)
+    mv = batch
+    while pos + 12 <= n:
+        ln = int.from_bytes(mv[pos:pos + 8].tobytes(), "little")
+        pos += 16 + ln
+        offs.append(pos)
+    offs = np.array(offs[:-1] if offs[-1] > n else offs)
+    out = []
+    for i in range(n_slices):
+        start_target = (i * max(1, (n - slice_bytes)) // max(1, n_slices)) if n > slice_bytes else 0
+        si = int(np.searchsorted(offs, start_target))
+        s = int(offs[min(si, len(offs) - 1)])
+        ei = int(np.searchsorted(offs, min(n, s + slice_bytes), side="right")) - 1
+        e = int(offs[max(ei, si)])
+        if e <= s:
+            s, e = 0, int(offs[-1])
+        out.append((s, e))
+    return out
+
+
+def cpu_pass(schema, batch, slices, threads):
+    """every thread decodes its slice with the oracle; returns (bytes, seconds)"""
+    from oracle import oracle
+    oracle.lib()
+    errs = []
+
+    def work(i):
+        s, e = slices[i]
+        r = oracle.decode(batch[s:e], schema, copy_columns=False)
+        if r.info["error_code"] != 0:
+            errs.append(r.info)
+
+    ths = [threading.Thread(target=work, args=(i,)) for i in range(threads)]
+    t0 = time.perf_counter()
+    for t in ths:
+        t.start()
+    for t in ths:
+        t.join()
+    dt = time.perf_counter() - t0
+    assert not errs, errs
+    return sum(e - s for s, e in slices[:threads]), dt
+
+
+def run_reference(args):
+    rank, world, local = dist_env()
+    if rank != 0:
+        return
+    cores = host_cores()
+    sample = args.cpu_sample_mib << 20
+    schema, n, batches = make_batches(max(64, min(args.batch_mib, 256)), 1, seed=2024)
+    batch = batches[0]
+    slices = record_aligned_slices(batch, cores, sample)
+    for _ in range(args.warmup):
+        cpu_pass(schema, batch, slices, cores)
+    tot_b, tot_t = 0, 0.0
+    for _ in range(args.steps):
+        b, dt = cpu_pass(schema, batch, slices, cores)
+        tot_b += b
+        tot_t += dt
+    v = tot_b / tot_t / 1e9
+    line = {
+        "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * tot_t / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u8", "data": "synthetic", "impl": "reference",
+        "config": workload_config(args, n, int(len(batch)), extra={"arm": "CPU port of the reference path (oracle/tfr_oracle.c); the JVM reference cannot run here (no JDK)"}),
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"{cores} threads x {sample >> 20} MiB record-aligned slices of one batch per step"},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def workload_config(args, n_records, batch_bytes, extra=None):
+    c = {"workload": "configs[1]: Example decode, 32xInt64List[1] + 16xFloatList[8] + 16xBytesList[1](16 B), CRC verified, -> Arrow columns",
+         "records_per_step": n_records, "framed_bytes_per_step": batch_bytes,
+         "mean_framed_record_bytes": round(batch_bytes / max(1, n_records), 1),
+         "l2": "each step's input (>= 256 MiB) is larger than the 126 MB L2; batches cycle through a pool",
+         "pool_batches": args.pool}
+    if extra:
+        c.update(extra)
+    return c
+
+
+# ---------------------------------------------------------------------------------------------
+# clocks
+# ---------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            p = [x.strip() for x in ln.split(",")]
+            if len(p) < 6:
+                continue
+            try:
+                sm.append(float(p[0])); mx = float(p[1])
+            except ValueError:
+                continue
+            for nm, v in zip(names, p[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------
+# our arm
+# ---------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    from spark_tfrecord_b200 import _native
+    _native.lib()      # fails loudly when libtfrgpu.so is missing
+    rank, world, local = dist_env()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; there is no CPU fallback for the product path")
+    torch.cuda.set_device(local)
+    dev = local
+    use_dist = world > 1
+    if use_dist:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        if use_dist:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    schema, n_rec, batches = make_batches(args.batch_mib, args.pool, seed=2024 + 7919 * rank)
+    batch_bytes = [int(b.nbytes) for b in batches]
+    d_batches = [torch.from_numpy(b.copy()).cuda(dev) for b in batches]
+
+    # ---------------- resident path: the metric ----------------
+    dec = _native.Decoder(schema, 0, dev)
+    stream = torch.cuda.ExternalStream(dec.stream(), device=dev)
+    out_bytes = 0
+    for i in range(args.warmup):
+        b, used = dec.decode(d_batches[i % len(d_batches)])
+        assert used == batch_bytes[i % len(d_batches)] and b.info["error_code"] == 0, b.info
+        b.wait()
+        out_bytes = b.info["out_bytes"]
+        b.release()
+    dec.set_profiling(True)
+    clocks = ClockSampler(dev)
+    barrier()
+    clocks.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_wall0 = time.perf_counter()
+    ev0.record(stream)
+    in_bytes = 0
+    for i in range(args.steps):
+        k = i % len(d_batches)
+        b, used = dec.decode(d_batches[k])
+        b.release()                       # stream-ordered frees; the work itself stays enqueued
+        in_bytes += used
+    ev1.record(stream)
+    barrier()
+    t_wall = time.perf_counter() - t_wall0
+    clk = clocks.stop()
+    ms = ev0.elapsed_time(ev1)
+    prof = dec.get_profile()
+    dec.set_profiling(False)
+
+    # ---------------- end to end: pinned host -> device -> pinned host ----------------
+    e2e = None
+    if not args.no_e2e:
+        n_workers = 3
+        decs = [_native.Decoder(schema, 0, dev) for _ in range(n_workers)]
+        stages = []
+        for w, d in enumerate(decs):
+            src = batches[w % len(batches)]
+            st = d.staging(src.nbytes)
+            st[: src.nbytes] = src          # the JVM side writes file bytes here; not part of the timed region
+            stages.append((st, src.nbytes))
+        d2h = [0]
+
+        def e2e_steps(steps, w):
+            d = decs[w]
+            st, nb = stages[w]
+            for i in range(w, steps, n_workers):
+                b, used = d.decode(st, nbytes=nb)          # H2D from pinned memory + kernels
+                cols = b.to_host_raw()                     # D2H of every Arrow buffer into pinned memory
+                assert b.info["error_code"] == 0 and used == nb
+                if i == w:
+                    d2h[0] = b.info["out_bytes"]
+                b.release()
+
+        def run_e2e(steps):
+            ths = [threading.Thread(target=e2e_steps, args=(steps, w)) for w in range(n_workers)]
+            for t in ths:
+                t.start()
+            for t in ths:
+                t.join()
+
+        run_e2e(max(args.warmup, n_workers))
+        barrier()
+        t0 = time.perf_counter()
+        run_e2e(args.steps)
+        torch.cuda.synchronize()
+        barrier()
+        t_e2e = time.perf_counter() - t0
+        e2e_bytes = sum(stages[i % n_workers][1] for i in range(args.steps))
+        e2e = (e2e_bytes, t_e2e, d2h[0])
+        for d in decs:
+            d.close()
+
+    # ---------------- reduce over ranks ----------------
+    if use_dist:
+        t = torch.tensor([ms, t_wall, e2e[1] if e2e else 0.0], dtype=torch.float64, device=f"cuda:{dev}")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        s = torch.tensor([float(in_bytes), float(e2e[0] if e2e else 0)], dtype=torch.float64, device=f"cuda:{dev}")
+        dist.all_reduce(s, op=dist.ReduceOp.SUM)
+        ms, t_wall, t_e2e_max = t.tolist()
+        tot_in, tot_e2e = s.tolist()
+    else:
+        tot_in, tot_e2e, t_e2e_max = float(in_bytes), float(e2e[0] if e2e else 0), (e2e[1] if e2e else 0.0)
+
+    if rank != 0:
+        if use_dist:
+            dist.destroy_process_group()
+        return
+
+    value = tot_in / (ms * 1e-3) / 1e9
+    # ---------------- roofline of the dominant kernel ----------------
+    peaks = {}
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            peaks = json.load(f)
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+    n_fix = 32
+    p1_alg = batch_bytes[0] + n_rec * n_fix * 8          # bytes pass 1 must read (framed input) + fixed-width values it writes
+    p1_ms = prof["ms"]["pass1"] / max(1, prof["pass1_launches"])
+    achieved = p1_alg / (p1_ms * 1e-3) / 1e9 if p1_ms > 0 else 0.0
+    stage_ms = {k: round(v / args.steps, 4) for k, v in prof["ms"].items()}
+    step_alg = batch_bytes[0] + out_bytes
+    roof = {"bound": "hbm", "kernel": "decode_pass1_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+            "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+            "algorithmic_bytes_per_launch": p1_alg, "kernel_ms_per_launch": p1_ms,
+            "share_of_step": p1_ms / (ms / args.steps) if ms > 0 else None}
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u8", "data": "synthetic",
+        "config": workload_config(args, n_rec, batch_bytes[0], extra={
+            "arrow_out_bytes_per_step": int(out_bytes),
+            "timing": "CUDA events on the decoder stream (value); wall clock around pipelined steps incl. copies (e2e); max over ranks",
+            "parallelism": f"file/block sharded, {world} rank(s), no collective on the data path"}),
+        "roofline": roof,
+        "step_hbm": {"algorithmic_bytes_per_step": int(step_alg), "achieved_GBps": step_alg / (ms / args.steps * 1e-3) / 1e9,
+                     "frac_of_peak": step_alg / (ms / args.steps * 1e-3) / 1e9 / peak, "stage_ms_per_step": stage_ms},
+        "clocks": clk,
+        "gpu_launches": int(prof["launches"]),
+        "wall_s_timed_region": t_wall,
+    }
+    if e2e:
+        line["e2e"] = {"value": tot_e2e / t_e2e_max / 1e9, "unit": UNIT, "h2d_bytes_per_step": int(batch_bytes[0]),
+                       "d2h_bytes_per_step": int(e2e[2]), "pipeline": "3 decoder handles (threads), pinned staging in, pinned Arrow buffers out"}
+    # ---------------- CPU baseline beside it (rank 0, N=1 only) ----------------
+    if not args.no_cpu and world == 1:
+        cores = host_cores()
+        sample = args.cpu_sample_mib << 20
+        slices = record_aligned_slices(batches[0], cores, sample)
+        cpu_pass(schema, batches[0], slices, cores)
+        tb, tt, passes = 0, 0.0, 0
+        while tt < 8.0 and passes < 40:
+            bb, dt = cpu_pass(schema, batches[0], slices, cores)
+            tb += bb
+            tt += dt
+            passes += 1
+        line["cpu_baseline"] = {"value": tb / tt / 1e9, "unit": UNIT, "cores": cores, "kind": "port",
+                                "sample": f"{cores} threads x {sample >> 20} MiB record-aligned slices, {tt:.1f} s of wall time"}
+    print(json.dumps(line))
+    dec.close()
+    if use_dist:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -128,8 +128,19 @@ int32_t tfr_decoder_staging(tfr_decoder*, size_t min_bytes, void** host_ptr, siz
 int32_t tfr_decode(tfr_decoder*, const void* data, size_t nbytes, int32_t data_on_device,
                    int32_t is_final, tfr_batch** out, size_t* consumed);
 
-/* same stages, exposed separately for measurement (bench.py times the resident path) */
 int32_t tfr_decoder_stream(tfr_decoder*, void** cuda_stream /* cudaStream_t */);
+
+/* Measurement hooks (bench.py): with profiling enabled the decoder brackets every stage with CUDA
+ * events on its own stream.  tfr_decoder_get_profile synchronises the stream and returns cumulative
+ * device milliseconds per stage since profiling was enabled:
+ *   ms[0] frame index (scan+check+repair+finish+emit)   ms[1] decode pass 1 (CRC + parse)
+ *   ms[2] scans + summary                               ms[3] decode pass 2 (variable-width emit)
+ *   ms[4] validity pack                                 ms[5] H2D of the input (host input only)
+ * plus the number of kernel launches and of pass-1 launches.                                  */
+#define TFR_PROFILE_STAGES 8
+int32_t tfr_decoder_set_profiling(tfr_decoder*, int32_t enable);
+int32_t tfr_decoder_get_profile(tfr_decoder*, double* ms /* [TFR_PROFILE_STAGES] */, int64_t* kernel_launches,
+                                int64_t* pass1_launches);
 
 int32_t tfr_batch_wait(tfr_batch*);
 typedef struct tfr_batch_info {

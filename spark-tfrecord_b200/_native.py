@@ -22,7 +22,7 @@ _LIB = None
 EXPORTS = [
     "tfr_abi_version", "tfr_status_string", "tfr_last_error", "tfr_schema_create", "tfr_schema_destroy",
     "tfr_schema_num_fields", "tfr_decoder_create", "tfr_decoder_destroy", "tfr_decoder_staging", "tfr_decode",
-    "tfr_decoder_stream", "tfr_batch_wait", "tfr_batch_status", "tfr_batch_num_columns", "tfr_batch_columns",
+    "tfr_decoder_stream", "tfr_decoder_set_profiling", "tfr_decoder_get_profile", "tfr_batch_wait", "tfr_batch_status", "tfr_batch_num_columns", "tfr_batch_columns",
     "tfr_batch_to_host", "tfr_batch_export_arrow_host", "tfr_batch_export_arrow_device", "tfr_batch_release",
     "tfr_encoder_create", "tfr_encoder_destroy", "tfr_encode", "tfr_encoder_result_host", "tfr_encoder_stream",
     "tfr_infer_create", "tfr_infer_update", "tfr_infer_result", "tfr_infer_name", "tfr_infer_destroy",
@@ -105,6 +105,8 @@ def lib():
         "tfr_decoder_staging": (i32, [vp, sz, P(vp), P(sz)]),
         "tfr_decode": (i32, [vp, vp, sz, i32, i32, P(vp), P(sz)]),
         "tfr_decoder_stream": (i32, [vp, P(vp)]),
+        "tfr_decoder_set_profiling": (i32, [vp, i32]),
+        "tfr_decoder_get_profile": (i32, [vp, P(C.c_double), P(i64), P(i64)]),
         "tfr_batch_wait": (i32, [vp]),
         "tfr_batch_status": (i32, [vp, P(tfr_batch_info)]),
         "tfr_batch_num_columns": (i32, [vp]),
@@ -251,6 +253,17 @@ class Decoder:
         p = C.c_void_p()
         _check(lib().tfr_decoder_stream(self.h, C.byref(p)))
         return p.value or 0
+
+    def set_profiling(self, enable: bool):
+        _check(lib().tfr_decoder_set_profiling(self.h, 1 if enable else 0))
+
+    def get_profile(self):
+        ms = (C.c_double * 8)()
+        nl = C.c_int64()
+        n1 = C.c_int64()
+        _check(lib().tfr_decoder_get_profile(self.h, ms, C.byref(nl), C.byref(n1)))
+        names = ["frame_index", "pass1", "scan", "pass2", "pack_validity", "h2d"]
+        return {"ms": {k: ms[i] for i, k in enumerate(names)}, "launches": nl.value, "pass1_launches": n1.value}
 
     def decode(self, data, is_final: bool = True, nbytes: Optional[int] = None):
         """-> (Batch, consumed_bytes)"""

@@ -262,6 +262,27 @@ struct tfr_decoder {
   void** h_ptr_tables = nullptr;        // pinned mirror of the device pointer tables
   size_t h_ptr_cap = 0;
   PinnedPool host_pool;
+  // profiling (bench.py): CUDA events around the stages
+  bool profiling = false;
+  struct Span { int stage; cudaEvent_t a, b; };
+  std::vector<Span> spans;
+  std::vector<cudaEvent_t> ev_pool;
+  double prof_ms[TFR_PROFILE_STAGES] = {0};
+  int64_t launches = 0, pass1_launches = 0;
+  cudaEvent_t ev_get() {
+    if (!ev_pool.empty()) { cudaEvent_t e = ev_pool.back(); ev_pool.pop_back(); return e; }
+    cudaEvent_t e; cudaEventCreate(&e); return e;
+  }
+  void span_begin(int stage) { if (!profiling) return; Span s{stage, ev_get(), nullptr}; cudaEventRecord(s.a, stream); spans.push_back(s); }
+  void span_end(int nlaunch) { launches += nlaunch; if (!profiling) return; Span& s = spans.back(); s.b = ev_get(); cudaEventRecord(s.b, stream); }
+  void spans_resolve() {
+    for (auto& s : spans) {
+      if (!s.b) { ev_pool.push_back(s.a); continue; }
+      float ms = 0; if (cudaEventElapsedTime(&ms, s.a, s.b) == cudaSuccess) prof_ms[s.stage] += ms;
+      ev_pool.push_back(s.a); ev_pool.push_back(s.b);
+    }
+    spans.clear();
+  }
 };
 
 struct Segment { void* dev; size_t bytes; size_t host_off; };
@@ -313,6 +334,8 @@ static void decoder_unref(tfr_decoder* d) {
   cudaFreeHost(d->h_stats); cudaFreeHost(d->h_totals);
   if (d->h_ptr_tables) cudaFreeHost(d->h_ptr_tables);
   d->host_pool.release_all();
+  d->spans_resolve();
+  for (cudaEvent_t e : d->ev_pool) cudaEventDestroy(e);
   cudaStreamDestroy(d->stream);
   delete d;
 }
@@ -329,6 +352,26 @@ extern "C" int32_t tfr_decoder_staging(tfr_decoder* d, size_t min_bytes, void** 
   }
   *host_ptr = d->staging;
   if (capacity) *capacity = d->staging_cap;
+  return TFR_OK;
+}
+extern "C" int32_t tfr_decoder_set_profiling(tfr_decoder* d, int32_t enable) {
+  if (!d) return TFR_E_INVALID_ARG;
+  cudaSetDevice(d->device);
+  cudaStreamSynchronize(d->stream);
+  d->spans_resolve();
+  d->profiling = enable != 0;
+  for (double& m : d->prof_ms) m = 0;
+  d->launches = 0; d->pass1_launches = 0;
+  return TFR_OK;
+}
+extern "C" int32_t tfr_decoder_get_profile(tfr_decoder* d, double* ms, int64_t* launches, int64_t* pass1) {
+  if (!d || !ms) return TFR_E_INVALID_ARG;
+  CUDA_TRY(cudaSetDevice(d->device));
+  CUDA_TRY(cudaStreamSynchronize(d->stream));
+  d->spans_resolve();
+  for (int i = 0; i < TFR_PROFILE_STAGES; ++i) ms[i] = d->prof_ms[i];
+  if (launches) *launches = d->launches;
+  if (pass1) *pass1 = d->pass1_launches;
   return TFR_OK;
 }
 extern "C" int32_t tfr_decoder_stream(tfr_decoder* d, void** s) { if (!d || !s) return TFR_E_INVALID_ARG; *s = d->stream; return TFR_OK; }
@@ -369,7 +412,9 @@ extern "C" int32_t tfr_decode(tfr_decoder* d, const void* data, size_t nbytes, i
   const uint8_t* d_data = (const uint8_t*)data;
   if (!data_on_device && nbytes) {
     TRY(d->in.ensure(align_up(nbytes + 16, 256)));
+    d->span_begin(5);
     CUDA_TRY(cudaMemcpyAsync(d->in.p, data, nbytes, cudaMemcpyHostToDevice, st));
+    d->span_end(0);
     d_data = (const uint8_t*)d->in.p;
   }
   // ---- K1: record boundaries ----
@@ -387,10 +432,12 @@ extern "C" int32_t tfr_decode(tfr_decoder* d, const void* data, size_t nbytes, i
     d->h_stats->frame = init;
     CUDA_TRY(cudaMemcpyAsync(d_fr, &d->h_stats->frame, sizeof(FrameResult), cudaMemcpyHostToDevice, st));
     uint32_t grid = std::min<uint32_t>((n_chunks + 7) / 8, (uint32_t)d->ctx->sm_count * 8);
+    d->span_begin(0);
     frame_scan_kernel<<<grid, 256, 0, st>>>(d_data, (uint32_t)nbytes, chunk_bytes, n_chunks, verify, d->ctx->d_tabs, (ChunkInfo*)d->chunks.p);
     frame_check_kernel<<<(n_chunks + 255) / 256, 256, 0, st>>>((const ChunkInfo*)d->chunks.p, n_chunks, d_fr);
     frame_repair_kernel<<<1, 32, 0, st>>>(d_data, (uint32_t)nbytes, chunk_bytes, n_chunks, verify, d->ctx->d_tabs, (ChunkInfo*)d->chunks.p, d_fr);
     frame_finish_kernel<<<1, 1024, 0, st>>>((const ChunkInfo*)d->chunks.p, n_chunks, (uint32_t)nbytes, (uint32_t*)d->chunk_base.p, d_fr);
+    d->span_end(4);
     CUDA_TRY(cudaMemcpyAsync(&d->h_stats->frame, d_fr, sizeof(FrameResult), cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));                       // sync #1: number of records
     CUDA_TRY(cudaGetLastError());
@@ -445,8 +492,10 @@ extern "C" int32_t tfr_decode(tfr_decoder* d, const void* data, size_t nbytes, i
   if (n > 0) {
     TRY(d->rec_off.ensure(((size_t)n + 1) * 4));
     uint32_t grid = std::min<uint32_t>((n_chunks + 7) / 8, (uint32_t)d->ctx->sm_count * 8);
+    d->span_begin(0);
     frame_emit_kernel<<<grid, 256, 0, st>>>(d_data, (const ChunkInfo*)d->chunks.p, (const uint32_t*)d->chunk_base.p, n_chunks,
                                             (const FrameResult*)d->small.p, (uint32_t*)d->rec_off.p);
+    d->span_end(1);
     TRY(d->status.ensure((size_t)n * 4));
     TRY(d->valid8.ensure((size_t)n * std::max<uint32_t>(nf, 1) + 8));
     TRY(d->cnt.ensure((size_t)n * std::max<int>(S.n_cnt, 1) * 4));
@@ -473,7 +522,9 @@ extern "C" int32_t tfr_decode(tfr_decoder* d, const void* data, size_t nbytes, i
     const uint32_t warps = 8;
     size_t smem1 = CRC_SMEM_WORDS * 4 + (size_t)warps * ((nf + 3) & ~3u);
     uint32_t g1 = std::min<uint32_t>((n + warps - 1) / warps, (uint32_t)d->ctx->sm_count * 16);
+    d->span_begin(1);
     decode_pass1_kernel<<<g1, warps * 32, smem1, st>>>(A);
+    d->span_end(1); d->pass1_launches++;
 
     DecodeSummary* d_sum = (DecodeSummary*)((uint8_t*)d->small.p + 256);
     uint32_t* d_overflow = (uint32_t*)((uint8_t*)d->small.p + 512);
@@ -481,6 +532,7 @@ extern "C" int32_t tfr_decode(tfr_decoder* d, const void* data, size_t nbytes, i
     d->h_stats->summary = sum; d->h_stats->overflow = 0;
     CUDA_TRY(cudaMemcpyAsync(d_sum, &d->h_stats->summary, sizeof(DecodeSummary), cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaMemsetAsync(d_overflow, 0, 4, st));
+    d->span_begin(2);
     first_error_kernel<<<std::min<uint32_t>((n + 255) / 256, 1024), 256, 0, st>>>(A.status, n, d_sum);
     if (S.n_cnt > 0) {
       uint32_t n_tiles = (n + SCAN_TILE - 1) / SCAN_TILE;
@@ -492,6 +544,7 @@ extern "C" int32_t tfr_decode(tfr_decoder* d, const void* data, size_t nbytes, i
       scan_apply_kernel<<<dim3(n_tiles, S.n_cnt), SCAN_THREADS, 0, st>>>(A.cnt, n, n_tiles, tsum, traw, (int32_t* const*)dt_scan);
     }
     summary_kernel<<<1, 256, 0, st>>>(A.status, A.rec_off, n, d_sum, (const int32_t* const*)dt_scan, (uint32_t)S.n_cnt, d_totals);
+    d->span_end(S.n_cnt > 0 ? 5 : 2);
     CUDA_TRY(cudaMemcpyAsync(&d->h_stats->summary, d_sum, sizeof(DecodeSummary), cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaMemcpyAsync(&d->h_stats->overflow, d_overflow, 4, cudaMemcpyDeviceToHost, st));
     if (S.n_cnt) CUDA_TRY(cudaMemcpyAsync(totals, d_totals, (size_t)S.n_cnt * 8, cudaMemcpyDeviceToHost, st));
@@ -531,13 +584,17 @@ extern "C" int32_t tfr_decode(tfr_decoder* d, const void* data, size_t nbytes, i
     A.var_field = d->dsch.d_var_field;
     if (n_eff > 0 && S.n_var > 0) {
       uint32_t g2 = std::min<uint32_t>((n_eff + warps - 1) / warps, (uint32_t)d->ctx->sm_count * 16);
+      d->span_begin(3);
       decode_pass2_kernel<<<g2, warps * 32, 0, st>>>(A);
+      d->span_end(1);
     }
     if (n_eff > 0 && nf > 0) {
       uint32_t nbytes_bm = (n_eff + 7) / 8;
       dim3 g((nbytes_bm + 255) / 256, nf);
       g.x = std::min<uint32_t>(g.x, 4096);
+      d->span_begin(4);
       pack_validity_kernel<<<g, 256, 0, st>>>(A.valid8, n, n_eff, nf, nb_stride, fx + bitmaps_off, b->d_null_counts);
+      d->span_end(1);
     }
     // device column views
     b->cols.resize(nf);
