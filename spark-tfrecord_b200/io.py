@@ -1,0 +1,251 @@
+"""Host-side mirror of the reference interface for the hot path, by name.
+
+    reference (Scala)                                   here
+    ------------------------------------------------    ---------------------------------------------
+    TFRecordFileReader.readFile(conf, options, file,    TFRecordFileReader.readFile(conf, options, file, schema)
+        schema): Iterator[InternalRow]                      -> iterator of row tuples
+        (M/TFRecordFileReader.scala:16-83)
+    new TFRecordDeserializer(schema).deserializeExample TFRecordDeserializer(schema).deserializeExample(bytes)
+        (M/TFRecordDeserializer.scala:21-61)
+    new TFRecordSerializer(schema).serializeExample     TFRecordSerializer(schema).serializeExample(row) -> bytes
+        (M/TFRecordSerializer.scala:20-60)
+    new TFRecordOutputWriter(path, options, schema,     TFRecordOutputWriter(path, options, dataSchema, context)
+        context).write(row)/close()                         .write(row) / .close()
+        (M/TFRecordOutputWriter.scala:12-44)
+    DefaultSource (M/DefaultSource.scala:23-143)        DefaultSource: shortName/isSplitable/buildReader/prepareWrite
+
+Everything that touches record bytes goes through the C ABI (libtfrgpu.so): there is no Python or CPU
+implementation of the path in this package.  Rows are tuples of Python values (None, int, float, str,
+bytes, list, list of lists) standing in for Catalyst's InternalRow; message arguments are serialized
+protobuf bytes (there are no org.tensorflow.example classes here)."""
+from __future__ import annotations
+
+import os
+import struct
+from typing import Dict, Iterator, List, Optional, Sequence
+
+import numpy as np
+
+from . import _native
+from ._cabi import TFR_F_DEFAULT, columns_from_rows
+from .sqltypes import RECORD_TYPES, StructType, byte_array_schema
+
+M = "src/main/scala/com/linkedin/spark/datasources/tfrecord/"
+
+
+def _record_type(options: Optional[Dict[str, str]]) -> int:
+    rt = (options or {}).get("recordType", "Example")          # M/TFRecordFileReader.scala:22
+    if rt not in RECORD_TYPES:                                  # :78-79
+        raise _native.IllegalArgumentException(-3, f"Unsupported recordType {rt}: recordType can be ByteArray, Example or SequenceExample")
+    return RECORD_TYPES[rt]
+
+
+def _rows_of(batch: "_native.Batch") -> List[tuple]:
+    cols = batch.to_host()
+    return [tuple(c.get(r) for c in cols) for r in range(batch.n_rows)]
+
+
+class TFRecordDeserializer:
+    """One record at a time, like the reference class; each call is one tfr_decode of a single frame (CRC
+    check off: the payload never went through TFRecordReader here)."""
+
+    def __init__(self, dataSchema: StructType, device: int = 0):
+        self.schema = dataSchema
+        self.device = device
+        self._dec: Dict[int, _native.Decoder] = {}
+
+    def _decoder(self, rt: int) -> "_native.Decoder":
+        if rt not in self._dec:
+            self._dec[rt] = _native.Decoder(self.schema, rt, self.device, flags=0)
+        return self._dec[rt]
+
+    def _one(self, payload: bytes, rt: int) -> tuple:
+        frame = struct.pack("<QI", len(payload), 0) + bytes(payload) + b"\0\0\0\0"
+        batch, _ = self._decoder(rt).decode(frame)
+        try:
+            batch.raise_if_error()
+            return _rows_of(batch)[0]
+        finally:
+            batch.release()
+
+    def deserializeByteArray(self, byteArray: bytes) -> tuple:
+        return self._one(byteArray, 2)
+
+    def deserializeExample(self, example: bytes) -> tuple:
+        return self._one(example, 0)
+
+    def deserializeSequenceExample(self, sequenceExample: bytes) -> tuple:
+        return self._one(sequenceExample, 1)
+
+    def close(self):
+        for d in self._dec.values():
+            d.close()
+        self._dec = {}
+
+
+class TFRecordSerializer:
+    """Constructor validates the types like the reference's (featureConverters are built eagerly,
+    M/TFRecordSerializer.scala:14 -> RuntimeException for unsupported types)."""
+
+    def __init__(self, dataSchema: StructType, device: int = 0):
+        self.schema = dataSchema
+        self.device = device
+        self._enc: Dict[int, _native.Encoder] = {}
+        _native.Schema(dataSchema, 1).close()        # type validation only
+
+    def _encoder(self, rt: int) -> "_native.Encoder":
+        if rt not in self._enc:
+            schema = byte_array_schema() if rt == 2 else self.schema
+            self._enc[rt] = _native.Encoder(schema, rt, self.device)
+        return self._enc[rt]
+
+    def _one(self, row: Sequence, rt: int) -> bytes:
+        schema = byte_array_schema() if rt == 2 else self.schema
+        framed = self._encoder(rt).encode(columns_from_rows(schema, [tuple(row)], rt))
+        return framed[12:-4]
+
+    def serializeByteArray(self, row: Sequence) -> bytes:
+        return self._one(row, 2)
+
+    def serializeExample(self, row: Sequence) -> bytes:
+        return self._one(row, 0)
+
+    def serializeSequenceExample(self, row: Sequence) -> bytes:
+        return self._one(row, 1)
+
+    def close(self):
+        for e in self._enc.values():
+            e.close()
+        self._enc = {}
+
+
+class PartitionedFile:
+    def __init__(self, filePath: str, start: int = 0, length: Optional[int] = None):
+        self.filePath = filePath
+        self.start = start
+        self.length = os.path.getsize(filePath) if length is None else length
+
+    def toPath(self):
+        return self.filePath
+
+
+class TFRecordFileReader:
+    BLOCK_BYTES = 256 << 20
+
+    @staticmethod
+    def readFile(conf, options: Dict[str, str], file: PartitionedFile, schema: StructType, device: int = 0,
+                 block_bytes: Optional[int] = None) -> Iterator[tuple]:
+        """Stages the file in blocks into the decoder's pinned buffer and decodes each block on the GPU; the
+        unconsumed tail of a block (a partial record) is carried into the next one.  Rows before a bad
+        record are yielded, then the exception the reference would throw is raised."""
+        rt = _record_type(options)
+        block = block_bytes or TFRecordFileReader.BLOCK_BYTES
+        dec = _native.Decoder(schema, rt, device, TFR_F_DEFAULT)
+
+        def gen():
+            try:
+                with open(file.toPath(), "rb") as f:
+                    f.seek(file.start)
+                    remaining = file.length
+                    carry = b""
+                    while True:
+                        want = min(max(block - len(carry), block // 2), remaining)   # a carried record larger than the block still makes progress
+                        chunk = f.read(want) if want > 0 else b""
+                        remaining -= len(chunk)
+                        final = remaining == 0 or len(chunk) < want
+                        nbytes = len(carry) + len(chunk)
+                        st = dec.staging(max(nbytes, 1))
+                        if carry:
+                            st[: len(carry)] = np.frombuffer(carry, dtype=np.uint8)
+                        if chunk:
+                            st[len(carry): nbytes] = np.frombuffer(chunk, dtype=np.uint8)
+                        batch, used = dec.decode(st, is_final=final, nbytes=nbytes)
+                        try:
+                            for row in _rows_of(batch):
+                                yield row
+                            batch.raise_if_error()
+                        finally:
+                            batch.release()
+                        carry = st[used:nbytes].tobytes()
+                        if final:
+                            return
+            finally:
+                dec.close()
+
+        return gen()
+
+
+class TFRecordOutputWriter:
+    FLUSH_ROWS = 1 << 16
+
+    def __init__(self, path: str, options: Dict[str, str], dataSchema: StructType, context=None, device: int = 0):
+        self.path = path
+        self.recordType = _record_type(options)                 # validated up front; the reference throws at the first write
+        self.schema = byte_array_schema() if self.recordType == 2 else dataSchema
+        self._enc = _native.Encoder(self.schema, self.recordType, device)
+        self._rows: List[tuple] = []
+        self._out = open(path, "wb")                            # CodecStreams.createOutputStream (no codec here)
+
+    def write(self, row: Sequence) -> None:
+        self._rows.append(tuple(row))
+        if len(self._rows) >= self.FLUSH_ROWS:
+            self._flush()
+
+    def _flush(self):
+        if self._rows:
+            cols = columns_from_rows(self.schema, self._rows, self.recordType)
+            self._out.write(self._enc.encode(cols))
+            self._rows = []
+
+    def close(self) -> None:
+        try:
+            self._flush()
+        finally:
+            self._out.close()
+            self._enc.close()
+
+
+class DefaultSource:
+    """The FileFormat surface that stays (M/DefaultSource.scala:23-143): names and meanings only."""
+
+    def shortName(self) -> str:
+        return "tfrecord"
+
+    def isSplitable(self, *a, **k) -> bool:
+        return False                                             # :26-29; splitting happens inside the native side
+
+    def buildReader(self, dataSchema: StructType, requiredSchema: StructType, options: Dict[str, str], device: int = 0):
+        """-> PartitionedFile => Iterator[row] (filters are accepted and ignored, :123)"""
+        return lambda file: TFRecordFileReader.readFile(None, options, file, requiredSchema, device)
+
+    def prepareWrite(self, options: Dict[str, str], dataSchema: StructType):
+        codec = (options or {}).get("codec", "")
+        if codec:
+            raise NotImplementedError("codec: stream compression stays on the JVM side (CodecStreams), out of scope here")
+
+        class _Factory:
+            def newInstance(self_inner, path, schema, context=None):
+                return TFRecordOutputWriter(path, options, schema, context)
+
+            def getFileExtension(self_inner, context=None):
+                return ".tfrecord"
+
+        return _Factory()
+
+    # convenience used by the tests: spark.read.format("tfrecord").schema(s).load(p) / df.write...save(p)
+    def load(self, path: str, schema: StructType, options: Optional[Dict[str, str]] = None, device: int = 0) -> List[tuple]:
+        files = [path] if os.path.isfile(path) else sorted(os.path.join(path, f) for f in os.listdir(path)
+                                                           if not f.startswith(("_", ".")))
+        reader = self.buildReader(schema, schema, options or {}, device)
+        rows: List[tuple] = []
+        for f in files:
+            rows.extend(reader(PartitionedFile(f)))
+        return rows
+
+    def save(self, path: str, schema: StructType, rows: Sequence[Sequence], options: Optional[Dict[str, str]] = None) -> None:
+        os.makedirs(path, exist_ok=True)
+        w = self.prepareWrite(options or {}, schema).newInstance(os.path.join(path, "part-00000.tfrecord"), schema)
+        for r in rows:
+            w.write(r)
+        w.close()
+        open(os.path.join(path, "_SUCCESS"), "wb").close()
