@@ -241,6 +241,7 @@ def test_io_bytearray_read_write(io, tmp_path):                               # 
 
 
 def test_bad_record_type_option(io, tmp_path):                                # M/TFRecordFileReader.scala:78-79
+    (tmp_path / "part-0.tfrecord").write_bytes(pyref.frame(b""))
     with pytest.raises(io.native.IllegalArgumentException):
         io.DefaultSource().load(str(tmp_path), exampleSchema, {"recordType": "Avro"})
 
