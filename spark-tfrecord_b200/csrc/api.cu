@@ -19,6 +19,7 @@
 #include "frame.cuh"
 #include "host_util.h"
 #include "scan.cuh"
+#include "tile.cuh"
 
 // ---------------------------------------------------------------------------------------------
 // errors
@@ -99,6 +100,10 @@ static void build_crc_tables(CrcTables& t) {
   for (int s = 0; s < 4; ++s)
     for (uint32_t b = 0; b < 256; ++b) t.k128[s][b] = mulmod(x128, b << (8 * s));
   for (uint32_t k = 0; k < 40; ++k) t.xw[k] = xpow_bytes(4 * k);
+  for (uint32_t i = 0; i < 256; ++i) {
+    t.s8[0][i] = t.t0[i];
+    for (int k = 1; k < 8; ++k) t.s8[k][i] = (t.s8[k - 1][i] >> 8) ^ t.t0[t.s8[k - 1][i] & 0xff];
+  }
 }
 
 static int32_t get_ctx(int device, DeviceCtx** out) {
@@ -262,6 +267,13 @@ struct tfr_decoder {
   void** h_ptr_tables = nullptr;        // pinned mirror of the device pointer tables
   size_t h_ptr_cap = 0;
   PinnedPool host_pool;
+  // fast path (tile.cuh)
+  bool fast_ok = false;
+  uint32_t tile_bytes = 49152, tile_threads = 32;
+  int spec_state = 0;                   // 0 learning, 1 speculating on uniform shapes, -1 disabled
+  std::vector<int32_t> spec_len;
+  DevBuf uniform_dev;
+  int32_t* h_uniform = nullptr;         // pinned
   // profiling (bench.py): CUDA events around the stages
   bool profiling = false;
   struct Span { int stage; cudaEvent_t a, b; };
@@ -313,9 +325,20 @@ extern "C" int32_t tfr_decoder_create(const tfr_schema* schema, int32_t device, 
   CUDA_TRY(cudaStreamCreateWithFlags(&d->stream, cudaStreamNonBlocking));
   rc = d->dsch.upload(d->schema);
   if (rc) { delete d; return rc; }
-  TRY(d->small.ensure(4096 + (size_t)d->schema.n_cnt * 8));
+  TRY(d->small.ensure(4096 + (size_t)d->schema.n_cnt * 16));
+  {
+    // fast path eligibility (tile.cuh): Example records, scalars and 1-D arrays, at most 128 fields
+    bool ok = d->schema.record_type == TFR_RT_EXAMPLE && d->schema.fields.size() <= 128 && !getenv("TFR_DISABLE_FAST");
+    for (const DevField& f : d->schema.fields) if (f.depth > 1) ok = false;
+    d->fast_ok = ok;
+    if (const char* e = getenv("TFR_TILE_KB")) { int kb = atoi(e); if (kb >= 16 && kb <= 192) d->tile_bytes = (uint32_t)kb * 1024; }
+    if (const char* e = getenv("TFR_TILE_THREADS")) { int t = atoi(e); if (t == 32 || t == 64 || t == 128) d->tile_threads = (uint32_t)t; }
+    if (getenv("TFR_DISABLE_SPECULATION")) d->spec_state = -1;
+    d->spec_len.assign(std::max(1, d->schema.n_var), -1);
+    CUDA_TRY(cudaHostAlloc((void**)&d->h_uniform, std::max<size_t>(1, d->schema.n_var) * 4, cudaHostAllocDefault));
+  }
   CUDA_TRY(cudaHostAlloc((void**)&d->h_stats, sizeof(HostStats), cudaHostAllocDefault));
-  size_t nt = (size_t)d->schema.n_cnt + d->schema.fields.size() + 8;
+  size_t nt = (size_t)d->schema.n_cnt * 2 + d->schema.fields.size() + 8;
   CUDA_TRY(cudaHostAlloc((void**)&d->h_totals, nt * sizeof(int64_t), cudaHostAllocDefault));
   *out = d;
   return TFR_OK;
@@ -327,11 +350,12 @@ static void decoder_unref(tfr_decoder* d) {
   cudaSetDevice(d->device);
   cudaStreamSynchronize(d->stream);
   for (DevBuf* b : {&d->in, &d->chunks, &d->chunk_base, &d->rec_off, &d->status, &d->valid8, &d->cnt, &d->src, &d->cflag, &d->tsum,
-                    &d->scan_scratch, &d->ptr_tables, &d->small})
+                    &d->scan_scratch, &d->ptr_tables, &d->small, &d->uniform_dev})
     b->release();
   d->dsch.free_all();
   if (d->staging) cudaFreeHost(d->staging);
   cudaFreeHost(d->h_stats); cudaFreeHost(d->h_totals);
+  if (d->h_uniform) cudaFreeHost(d->h_uniform);
   if (d->h_ptr_tables) cudaFreeHost(d->h_ptr_tables);
   d->host_pool.release_all();
   d->spans_resolve();
@@ -393,6 +417,205 @@ static uint32_t pick_chunk_bytes(size_t nbytes, int sm_count) {
   return (uint32_t)c;
 }
 
+// everything one tfr_decode call needs across its stages
+struct DecodeCtx {
+  tfr_decoder* d; tfr_batch* b; cudaStream_t st;
+  const uint8_t* d_data; size_t nbytes;
+  uint32_t n = 0, n_chunks = 0, chunk_bytes = 0, verify = 0, nf = 0, nb_stride = 0;
+  std::vector<size_t> fix_off, off0_off;
+  size_t bitmaps_off = 0, nullc_off = 0;
+  uint8_t* fx = nullptr;
+  void **t_fix, **t_scan, **t_offs, **t_vals, **dt_fix, **dt_scan, **dt_offs, **dt_vals;
+  bool rec_off_ready = false;
+};
+
+static int32_t alloc_fixed(DecodeCtx& C) {
+  tfr_decoder* d = C.d; const tfr_schema& S = d->schema; const uint32_t n = C.n, nf = C.nf;
+  C.nb_stride = (uint32_t)align_up(((size_t)n + 7) / 8 + 1, 64);
+  C.fix_off.assign(S.n_fix, 0); C.off0_off.assign(S.n_var, 0);
+  size_t fixed_bytes = 0;
+  C.bitmaps_off = 0; fixed_bytes += align_up((size_t)C.nb_stride * std::max<uint32_t>(nf, 1), 256);
+  C.nullc_off = fixed_bytes; fixed_bytes += align_up(sizeof(unsigned long long) * std::max<uint32_t>(nf, 1), 256);
+  for (int i = 0; i < S.n_fix; ++i) { C.fix_off[i] = fixed_bytes; fixed_bytes += align_up((size_t)n * S.fields[S.fix_field[i]].width + 8, 256); }
+  for (int v = 0; v < S.n_var; ++v) { C.off0_off[v] = fixed_bytes; fixed_bytes += align_up(((size_t)n + 1) * 4, 256); }
+  CUDA_TRY(cudaMallocAsync(&C.b->dev_fixed, fixed_bytes, C.st));
+  C.b->dev_fixed_bytes = fixed_bytes;
+  C.fx = (uint8_t*)C.b->dev_fixed;
+  C.b->d_null_counts = (unsigned long long*)(C.fx + C.nullc_off);
+  CUDA_TRY(cudaMemsetAsync(C.fx + C.nullc_off, 0, sizeof(unsigned long long) * std::max<uint32_t>(nf, 1), C.st));
+  if (n == 0) for (int v = 0; v < S.n_var; ++v) CUDA_TRY(cudaMemsetAsync(C.fx + C.off0_off[v], 0, 4, C.st));
+  // pointer tables
+  const size_t n_ptr = (size_t)S.n_fix + (size_t)S.n_cnt + (size_t)S.n_var * 4 + 8;
+  if (d->h_ptr_cap < n_ptr) {
+    if (d->h_ptr_tables) cudaFreeHost(d->h_ptr_tables);
+    CUDA_TRY(cudaHostAlloc((void**)&d->h_ptr_tables, n_ptr * sizeof(void*), cudaHostAllocDefault));
+    d->h_ptr_cap = n_ptr;
+  }
+  TRY(d->ptr_tables.ensure(n_ptr * sizeof(void*)));
+  void** hp = d->h_ptr_tables; void** dp = (void**)d->ptr_tables.p;
+  C.t_fix = hp;                        C.dt_fix = dp;
+  C.t_scan = hp + S.n_fix;             C.dt_scan = dp + S.n_fix;
+  C.t_offs = C.t_scan + S.n_cnt;       C.dt_offs = C.dt_scan + S.n_cnt;
+  C.t_vals = C.t_offs + S.n_var * 3;   C.dt_vals = C.dt_offs + S.n_var * 3;
+  return TFR_OK;
+}
+
+// scratch sized by n + scan output pointers + fixed value pointers, uploaded to the device tables
+static int32_t prepare_scratch(DecodeCtx& C) {
+  tfr_decoder* d = C.d; const tfr_schema& S = d->schema; const uint32_t n = C.n, nf = C.nf;
+  TRY(d->status.ensure((size_t)n * 4));
+  TRY(d->valid8.ensure((size_t)n * std::max<uint32_t>(nf, 1) + 8));
+  TRY(d->cnt.ensure((size_t)n * std::max<int>(S.n_cnt, 1) * 4));
+  TRY(d->src.ensure((size_t)n * std::max<int>(S.n_var, 1) * 4));
+  TRY(d->cflag.ensure((size_t)n * std::max<int>(S.n_var, 1)));
+  size_t deep = 0;
+  for (int v = 0; v < S.n_var; ++v) deep += (size_t)(S.fields[S.var_field[v]].n_levels - 1);
+  TRY(d->scan_scratch.ensure(deep * align_up(((size_t)n + 1) * 4, 256) + 256));
+  size_t so = 0;
+  for (int v = 0; v < S.n_var; ++v) {
+    const DevField& fd = S.fields[S.var_field[v]];
+    C.t_scan[fd.cnt_slot] = C.fx + C.off0_off[v];
+    for (int l = 1; l < fd.n_levels; ++l) { C.t_scan[fd.cnt_slot + l] = (uint8_t*)d->scan_scratch.p + so; so += align_up(((size_t)n + 1) * 4, 256); }
+  }
+  for (int i = 0; i < S.n_fix; ++i) C.t_fix[i] = C.fx + C.fix_off[i];
+  CUDA_TRY(cudaMemcpyAsync(C.dt_fix, C.t_fix, ((size_t)S.n_fix + S.n_cnt) * sizeof(void*), cudaMemcpyHostToDevice, C.st));
+  return TFR_OK;
+}
+
+static void fill_decode_args(DecodeCtx& C, DecodeArgs& A) {
+  tfr_decoder* d = C.d;
+  A = DecodeArgs{};
+  A.data = C.d_data; A.rec_off = (const uint32_t*)d->rec_off.p; A.n = C.n; A.nbytes = (uint32_t)C.nbytes; A.verify = C.verify;
+  A.sch = d->dsch.view; A.tabs = d->ctx->d_tabs;
+  A.status = (uint32_t*)d->status.p; A.valid8 = (uint8_t*)d->valid8.p; A.fix_values = (void* const*)C.dt_fix;
+  A.cnt = (uint32_t*)d->cnt.p; A.src = (uint32_t*)d->src.p; A.cflag = (uint8_t*)d->cflag.p;
+  A.scan = (const int32_t* const*)C.dt_scan; A.offs = (int32_t* const*)C.dt_offs; A.var_values = (void* const*)C.dt_vals;
+  A.var_field = d->dsch.d_var_field;
+}
+
+static int32_t ensure_rec_off(DecodeCtx& C) {
+  if (C.rec_off_ready) return TFR_OK;
+  tfr_decoder* d = C.d;
+  TRY(d->rec_off.ensure(((size_t)C.n + 1) * 4));
+  uint32_t grid = std::min<uint32_t>((C.n_chunks + 7) / 8, (uint32_t)d->ctx->sm_count * 8);
+  d->span_begin(0);
+  frame_emit_kernel<<<grid, 256, 0, C.st>>>(C.d_data, (const ChunkInfo*)d->chunks.p, (const uint32_t*)d->chunk_base.p, C.n_chunks,
+                                            (const FrameResult*)d->small.p, (uint32_t*)d->rec_off.p);
+  d->span_end(1);
+  C.rec_off_ready = true;
+  return TFR_OK;
+}
+
+// device scratch inside d->small: [0] FrameResult, [256] DecodeSummary, [512] overflow, [516] tile flags, [1024] totals, then first counts
+static DecodeSummary* dsum_ptr(tfr_decoder* d) { return (DecodeSummary*)((uint8_t*)d->small.p + 256); }
+static uint32_t* dovf_ptr(tfr_decoder* d) { return (uint32_t*)((uint8_t*)d->small.p + 512); }
+static uint32_t* dflags_ptr(tfr_decoder* d) { return (uint32_t*)((uint8_t*)d->small.p + 516); }
+static int64_t* dtot_ptr(tfr_decoder* d) { return (int64_t*)((uint8_t*)d->small.p + 1024); }
+
+// scans + summary + the one D2H that carries totals / first error / flags; leaves results in h_stats / h_totals
+static int32_t scans_and_sync(DecodeCtx& C, DecodeArgs& A, bool with_status) {
+  tfr_decoder* d = C.d; const tfr_schema& S = d->schema; const uint32_t n = C.n; cudaStream_t st = C.st;
+  DecodeSummary init{}; init.first_err_row = 0xffffffffu; init.n_eff = n;
+  d->h_stats->summary = init; d->h_stats->overflow = 0;
+  CUDA_TRY(cudaMemcpyAsync(dsum_ptr(d), &d->h_stats->summary, sizeof(DecodeSummary), cudaMemcpyHostToDevice, st));
+  CUDA_TRY(cudaMemsetAsync(dovf_ptr(d), 0, 4, st));
+  d->span_begin(2);
+  int nl = 0;
+  if (with_status) { first_error_kernel<<<std::min<uint32_t>((n + 255) / 256, 1024), 256, 0, st>>>(A.status, n, dsum_ptr(d)); ++nl; }
+  if (S.n_cnt > 0) {
+    uint32_t n_tiles = (n + SCAN_TILE - 1) / SCAN_TILE;
+    TRY(d->tsum.ensure(((size_t)S.n_cnt * n_tiles + S.n_cnt) * 8 + 64));
+    uint64_t* tsum = (uint64_t*)d->tsum.p;
+    uint64_t* traw = tsum + (size_t)S.n_cnt * n_tiles;
+    scan_tile_sums_kernel<<<dim3(n_tiles, S.n_cnt), SCAN_THREADS, 0, st>>>(A.cnt, n, n_tiles, tsum);
+    scan_tile_bases_kernel<<<S.n_cnt, 1024, 0, st>>>(tsum, n_tiles, traw, dovf_ptr(d));
+    scan_apply_kernel<<<dim3(n_tiles, S.n_cnt), SCAN_THREADS, 0, st>>>(A.cnt, n, n_tiles, tsum, traw, (int32_t* const*)C.dt_scan);
+    nl += 3;
+  }
+  summary_kernel<<<1, 256, 0, st>>>(with_status ? A.status : nullptr, with_status ? A.rec_off : nullptr, n, dsum_ptr(d), (const int32_t* const*)C.dt_scan, (uint32_t)S.n_cnt,
+                                    dtot_ptr(d), dtot_ptr(d) + S.n_cnt);
+  d->span_end(nl + 1);
+  CUDA_TRY(cudaMemcpyAsync(&d->h_stats->summary, dsum_ptr(d), sizeof(DecodeSummary), cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaMemcpyAsync(&d->h_stats->overflow, dovf_ptr(d), 8, cudaMemcpyDeviceToHost, st));   // overflow + tile flags
+  if (S.n_cnt) CUDA_TRY(cudaMemcpyAsync(d->h_totals, dtot_ptr(d), (size_t)S.n_cnt * 16, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  CUDA_TRY(cudaGetLastError());
+  return TFR_OK;
+}
+
+// variable-width outputs sized from totals, pass 2, validity pack, column views
+static int32_t finish_var_and_views(DecodeCtx& C, DecodeArgs& A, uint32_t n_eff, const int64_t* totals, bool run_pass2) {
+  tfr_decoder* d = C.d; const tfr_schema& S = d->schema; tfr_batch* b = C.b; cudaStream_t st = C.st; const uint32_t n = C.n, nf = C.nf;
+  std::vector<size_t> lvl_off((size_t)S.n_var * 3, 0), val_off(S.n_var, 0);
+  uint8_t* vx = (uint8_t*)b->dev_var;
+  if (run_pass2) {
+    size_t var_bytes = 0;
+    for (int v = 0; v < S.n_var; ++v) {
+      const DevField& fd = S.fields[S.var_field[v]];
+      for (int l = 1; l < fd.n_levels; ++l) { lvl_off[v * 3 + l] = var_bytes; var_bytes += align_up(((size_t)totals[fd.cnt_slot + l - 1] + 1) * 4, 256); }
+      val_off[v] = var_bytes; var_bytes += align_up((size_t)totals[fd.cnt_slot + fd.n_levels - 1] * fd.width + 8, 256);
+    }
+    if (var_bytes) CUDA_TRY(cudaMallocAsync(&b->dev_var, var_bytes, st));
+    b->dev_var_bytes = var_bytes;
+    vx = (uint8_t*)b->dev_var;
+    for (int v = 0; v < S.n_var; ++v) {
+      const DevField& fd = S.fields[S.var_field[v]];
+      C.t_offs[v * 3 + 0] = C.fx + C.off0_off[v];
+      for (int l = 1; l < 3; ++l) C.t_offs[v * 3 + l] = l < fd.n_levels ? vx + lvl_off[v * 3 + l] : nullptr;
+      for (int l = 1; l < fd.n_levels; ++l) CUDA_TRY(cudaMemsetAsync(vx + lvl_off[v * 3 + l], 0, 4, st));
+      C.t_vals[v] = vx + val_off[v];
+    }
+    CUDA_TRY(cudaMemcpyAsync(C.dt_offs, C.t_offs, ((size_t)S.n_var * 4) * sizeof(void*), cudaMemcpyHostToDevice, st));
+    A.n_eff = n_eff;
+    if (n_eff > 0 && S.n_var > 0) {
+      const uint32_t warps = 8;
+      uint32_t g2 = std::min<uint32_t>((n_eff + warps - 1) / warps, (uint32_t)d->ctx->sm_count * 16);
+      d->span_begin(3);
+      decode_pass2_kernel<<<g2, warps * 32, 0, st>>>(A);
+      d->span_end(1);
+    }
+  } else {
+    // uniform mode: the var block was allocated up front, one level per column
+    size_t off = 0;
+    for (int v = 0; v < S.n_var; ++v) { val_off[v] = off; off += align_up((size_t)totals[S.fields[S.var_field[v]].cnt_slot] * S.fields[S.var_field[v]].width + 8, 256); }
+  }
+  if (n_eff > 0 && nf > 0) {
+    uint32_t nbytes_bm = (n_eff + 7) / 8;
+    dim3 g((nbytes_bm + 255) / 256, nf);
+    g.x = std::min<uint32_t>(g.x, 4096);
+    d->span_begin(4);
+    pack_validity_kernel<<<g, 256, 0, st>>>((const uint8_t*)d->valid8.p, n, n_eff, nf, C.nb_stride, C.fx + C.bitmaps_off, b->d_null_counts);
+    d->span_end(1);
+  }
+  b->cols.resize(nf);
+  int64_t out_bytes = 0;
+  for (uint32_t f = 0; f < nf; ++f) {
+    const DevField& fd = S.fields[f];
+    tfr_column c{};
+    c.elem_type = fd.elem_type; c.depth = fd.depth; c.n_levels = fd.n_levels; c.value_width = fd.width;
+    c.n_rows = n_eff; c.validity = C.fx + C.bitmaps_off + (size_t)f * C.nb_stride;
+    out_bytes += (n_eff + 7) / 8;
+    if (fd.fix_slot >= 0) { c.values = C.fx + C.fix_off[fd.fix_slot]; c.n_values = n_eff; out_bytes += (int64_t)n_eff * fd.width; }
+    else if (fd.var_slot >= 0) {
+      int v = fd.var_slot;
+      c.offsets[0] = (int32_t*)(C.fx + C.off0_off[v]); c.n_offsets[0] = (int64_t)n_eff + 1;
+      for (int l = 1; l < fd.n_levels; ++l) { c.offsets[l] = (int32_t*)(vx + lvl_off[v * 3 + l]); c.n_offsets[l] = totals[fd.cnt_slot + l - 1] + 1; }
+      c.values = vx + val_off[v]; c.n_values = totals[fd.cnt_slot + fd.n_levels - 1];
+      for (int l = 0; l < fd.n_levels; ++l) out_bytes += c.n_offsets[l] * 4;
+      out_bytes += c.n_values * fd.width;
+    }
+    b->cols[f] = c;
+  }
+  b->info.out_bytes = out_bytes;
+  return TFR_OK;
+}
+
+template <int T>
+static void launch_tile(const TileArgs& TA, uint32_t smem, cudaStream_t st) {
+  cudaFuncSetAttribute(decode_tile_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  decode_tile_kernel<T><<<TA.n_chunks, T, smem, st>>>(TA);
+}
+
 extern "C" int32_t tfr_decode(tfr_decoder* d, const void* data, size_t nbytes, int32_t data_on_device, int32_t is_final, tfr_batch** out,
                               size_t* consumed) {
   if (!d || !out || (nbytes && !data)) return fail(TFR_E_INVALID_ARG, "null argument");
@@ -400,50 +623,51 @@ extern "C" int32_t tfr_decode(tfr_decoder* d, const void* data, size_t nbytes, i
   CUDA_TRY(cudaSetDevice(d->device));
   cudaStream_t st = d->stream;
   const tfr_schema& S = d->schema;
-  const uint32_t nf = (uint32_t)S.fields.size();
-  const uint32_t verify = (d->flags & TFR_F_VERIFY_CRC) ? 1u : 0u;
   auto* b = new tfr_batch;
   b->dec = d;
   d->refs.fetch_add(1);
   b->info.error_row = -1; b->info.error_field = -1;
   std::unique_ptr<tfr_batch, void (*)(tfr_batch*)> guard(b, [](tfr_batch* x) { tfr_batch_release(x); });
+  DecodeCtx C;
+  C.d = d; C.b = b; C.st = st; C.nbytes = nbytes; C.nf = (uint32_t)S.fields.size();
+  C.verify = (d->flags & TFR_F_VERIFY_CRC) ? 1u : 0u;
+  const uint32_t nf = C.nf;
 
   // ---- input ----
-  const uint8_t* d_data = (const uint8_t*)data;
+  C.d_data = (const uint8_t*)data;
   if (!data_on_device && nbytes) {
-    TRY(d->in.ensure(align_up(nbytes + 16, 256)));
+    TRY(d->in.ensure(align_up(nbytes + 64, 256)));
     d->span_begin(5);
     CUDA_TRY(cudaMemcpyAsync(d->in.p, data, nbytes, cudaMemcpyHostToDevice, st));
     d->span_end(0);
-    d_data = (const uint8_t*)d->in.p;
+    C.d_data = (const uint8_t*)d->in.p;
   }
   // ---- K1: record boundaries ----
-  uint32_t n = 0;
   FrameResult fr{};
   fr.stop = FS_EOF;
-  uint32_t n_chunks = 0, chunk_bytes = 0;
   if (nbytes) {
-    chunk_bytes = pick_chunk_bytes(nbytes, d->ctx->sm_count);
-    n_chunks = (uint32_t)((nbytes + chunk_bytes - 1) / chunk_bytes);
-    TRY(d->chunks.ensure((size_t)n_chunks * sizeof(ChunkInfo)));
-    TRY(d->chunk_base.ensure(((size_t)n_chunks + 1) * sizeof(uint32_t)));
+    C.chunk_bytes = d->fast_ok ? d->tile_bytes : pick_chunk_bytes(nbytes, d->ctx->sm_count);
+    C.n_chunks = (uint32_t)((nbytes + C.chunk_bytes - 1) / C.chunk_bytes);
+    TRY(d->chunks.ensure((size_t)C.n_chunks * sizeof(ChunkInfo)));
+    TRY(d->chunk_base.ensure(((size_t)C.n_chunks + 1) * sizeof(uint32_t)));
     FrameResult* d_fr = (FrameResult*)d->small.p;
     FrameResult init{}; init.first_bad = 0xffffffffu;
     d->h_stats->frame = init;
     CUDA_TRY(cudaMemcpyAsync(d_fr, &d->h_stats->frame, sizeof(FrameResult), cudaMemcpyHostToDevice, st));
-    uint32_t grid = std::min<uint32_t>((n_chunks + 7) / 8, (uint32_t)d->ctx->sm_count * 8);
+    uint32_t grid = std::min<uint32_t>((C.n_chunks + 7) / 8, (uint32_t)d->ctx->sm_count * 8);
     d->span_begin(0);
-    frame_scan_kernel<<<grid, 256, 0, st>>>(d_data, (uint32_t)nbytes, chunk_bytes, n_chunks, verify, d->ctx->d_tabs, (ChunkInfo*)d->chunks.p);
-    frame_check_kernel<<<(n_chunks + 255) / 256, 256, 0, st>>>((const ChunkInfo*)d->chunks.p, n_chunks, d_fr);
-    frame_repair_kernel<<<1, 32, 0, st>>>(d_data, (uint32_t)nbytes, chunk_bytes, n_chunks, verify, d->ctx->d_tabs, (ChunkInfo*)d->chunks.p, d_fr);
-    frame_finish_kernel<<<1, 1024, 0, st>>>((const ChunkInfo*)d->chunks.p, n_chunks, (uint32_t)nbytes, (uint32_t*)d->chunk_base.p, d_fr);
+    frame_scan_kernel<<<grid, 256, 0, st>>>(C.d_data, (uint32_t)nbytes, C.chunk_bytes, C.n_chunks, C.verify, d->ctx->d_tabs, (ChunkInfo*)d->chunks.p);
+    frame_check_kernel<<<(C.n_chunks + 255) / 256, 256, 0, st>>>((const ChunkInfo*)d->chunks.p, C.n_chunks, d_fr);
+    frame_repair_kernel<<<1, 32, 0, st>>>(C.d_data, (uint32_t)nbytes, C.chunk_bytes, C.n_chunks, C.verify, d->ctx->d_tabs, (ChunkInfo*)d->chunks.p, d_fr);
+    frame_finish_kernel<<<1, 1024, 0, st>>>((const ChunkInfo*)d->chunks.p, C.n_chunks, (uint32_t)nbytes, (uint32_t*)d->chunk_base.p, d_fr);
     d->span_end(4);
     CUDA_TRY(cudaMemcpyAsync(&d->h_stats->frame, d_fr, sizeof(FrameResult), cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));                       // sync #1: number of records
     CUDA_TRY(cudaGetLastError());
     fr = d->h_stats->frame;
-    n = fr.n_records;
+    C.n = fr.n_records;
   }
+  const uint32_t n = C.n;
   int32_t frame_err = frame_stop_to_error(fr.stop, is_final != 0);
   size_t used = nbytes;
   if (nbytes) {
@@ -453,170 +677,114 @@ extern "C" int32_t tfr_decode(tfr_decoder* d, const void* data, size_t nbytes, i
     else used = fr.stop_pos;                                   // partial tail of a non-final block is carried over
   }
   b->info.n_records = n; b->info.frame_repairs = (int32_t)fr.repairs;
-  if (consumed) *consumed = used;
-  b->info.consumed_bytes = (int64_t)used;
 
-  // ---- buffers that depend on n ----
-  const uint32_t nb_stride = (uint32_t)align_up(((size_t)n + 7) / 8 + 1, 64);
-  std::vector<size_t> fix_off(S.n_fix), off0_off(S.n_var);
-  size_t fixed_bytes = 0;
-  size_t bitmaps_off = 0; fixed_bytes += align_up((size_t)nb_stride * std::max<uint32_t>(nf, 1), 256);
-  size_t nullc_off = fixed_bytes; fixed_bytes += align_up(sizeof(unsigned long long) * std::max<uint32_t>(nf, 1), 256);
-  for (int i = 0; i < S.n_fix; ++i) { fix_off[i] = fixed_bytes; fixed_bytes += align_up((size_t)n * S.fields[S.fix_field[i]].width + 8, 256); }
-  for (int v = 0; v < S.n_var; ++v) { off0_off[v] = fixed_bytes; fixed_bytes += align_up(((size_t)n + 1) * 4, 256); }
-  CUDA_TRY(cudaMallocAsync(&b->dev_fixed, fixed_bytes, st));
-  b->dev_fixed_bytes = fixed_bytes;
-  uint8_t* fx = (uint8_t*)b->dev_fixed;
-  b->d_null_counts = (unsigned long long*)(fx + nullc_off);
-  CUDA_TRY(cudaMemsetAsync(fx + nullc_off, 0, sizeof(unsigned long long) * std::max<uint32_t>(nf, 1), st));
-  for (int v = 0; v < S.n_var; ++v) if (n == 0) CUDA_TRY(cudaMemsetAsync(fx + off0_off[v], 0, 4, st));
-
-  // pointer tables (device arrays of pointers used by the kernels), staged through pinned memory
-  const size_t n_ptr = (size_t)S.n_fix + (size_t)S.n_cnt + (size_t)S.n_var * 3 + (size_t)S.n_var + 8;
-  if (d->h_ptr_cap < n_ptr) {
-    if (d->h_ptr_tables) cudaFreeHost(d->h_ptr_tables);
-    CUDA_TRY(cudaHostAlloc((void**)&d->h_ptr_tables, n_ptr * sizeof(void*), cudaHostAllocDefault));
-    d->h_ptr_cap = n_ptr;
-  }
-  TRY(d->ptr_tables.ensure(n_ptr * sizeof(void*)));
-  void** hp = d->h_ptr_tables;
-  void** dp = (void**)d->ptr_tables.p;
-  void** t_fix = hp;                    void** dt_fix = dp;
-  void** t_scan = hp + S.n_fix;         void** dt_scan = dp + S.n_fix;
-  void** t_offs = t_scan + S.n_cnt;     void** dt_offs = dt_scan + S.n_cnt;
-  void** t_vals = t_offs + S.n_var * 3; void** dt_vals = dt_offs + S.n_var * 3;
-
-  int64_t* totals = d->h_totals;                      // [n_cnt]
+  TRY(alloc_fixed(C));
+  int64_t* totals = d->h_totals;                      // [n_cnt] totals at n_eff, then [n_cnt] first-row counts
   DecodeSummary sum{}; sum.first_err_row = 0xffffffffu; sum.n_eff = n;
   uint32_t n_eff = n;
   if (n > 0) {
-    TRY(d->rec_off.ensure(((size_t)n + 1) * 4));
-    uint32_t grid = std::min<uint32_t>((n_chunks + 7) / 8, (uint32_t)d->ctx->sm_count * 8);
-    d->span_begin(0);
-    frame_emit_kernel<<<grid, 256, 0, st>>>(d_data, (const ChunkInfo*)d->chunks.p, (const uint32_t*)d->chunk_base.p, n_chunks,
-                                            (const FrameResult*)d->small.p, (uint32_t*)d->rec_off.p);
-    d->span_end(1);
-    TRY(d->status.ensure((size_t)n * 4));
-    TRY(d->valid8.ensure((size_t)n * std::max<uint32_t>(nf, 1) + 8));
-    TRY(d->cnt.ensure((size_t)n * std::max<int>(S.n_cnt, 1) * 4));
-    TRY(d->src.ensure((size_t)n * std::max<int>(S.n_var, 1) * 4));
-    TRY(d->cflag.ensure((size_t)n * std::max<int>(S.n_var, 1)));
-    // scan outputs: level 0 -> the Arrow offsets in dev_fixed, deeper levels -> scratch
-    size_t deep = 0;
-    for (int v = 0; v < S.n_var; ++v) deep += (size_t)(S.fields[S.var_field[v]].n_levels - 1);
-    TRY(d->scan_scratch.ensure(deep * align_up(((size_t)n + 1) * 4, 256) + 256));
-    size_t so = 0;
-    for (int v = 0; v < S.n_var; ++v) {
-      const DevField& fd = S.fields[S.var_field[v]];
-      t_scan[fd.cnt_slot] = fx + off0_off[v];
-      for (int l = 1; l < fd.n_levels; ++l) { t_scan[fd.cnt_slot + l] = (uint8_t*)d->scan_scratch.p + so; so += align_up(((size_t)n + 1) * 4, 256); }
-    }
-    for (int i = 0; i < S.n_fix; ++i) t_fix[i] = fx + fix_off[i];
-    CUDA_TRY(cudaMemcpyAsync(dp, hp, ((size_t)S.n_fix + S.n_cnt) * sizeof(void*), cudaMemcpyHostToDevice, st));
-
-    DecodeArgs A{};
-    A.data = d_data; A.rec_off = (const uint32_t*)d->rec_off.p; A.n = n; A.verify = verify;
-    A.sch = d->dsch.view; A.tabs = d->ctx->d_tabs;
-    A.status = (uint32_t*)d->status.p; A.valid8 = (uint8_t*)d->valid8.p; A.fix_values = (void* const*)dt_fix;
-    A.cnt = (uint32_t*)d->cnt.p; A.src = (uint32_t*)d->src.p; A.cflag = (uint8_t*)d->cflag.p;
-    const uint32_t warps = 8;
-    size_t smem1 = CRC_SMEM_WORDS * 4 + (size_t)warps * ((nf + 3) & ~3u);
-    uint32_t g1 = std::min<uint32_t>((n + warps - 1) / warps, (uint32_t)d->ctx->sm_count * 16);
-    d->span_begin(1);
-    decode_pass1_kernel<<<g1, warps * 32, smem1, st>>>(A);
-    d->span_end(1); d->pass1_launches++;
-
-    DecodeSummary* d_sum = (DecodeSummary*)((uint8_t*)d->small.p + 256);
-    uint32_t* d_overflow = (uint32_t*)((uint8_t*)d->small.p + 512);
-    int64_t* d_totals = (int64_t*)((uint8_t*)d->small.p + 1024);
-    d->h_stats->summary = sum; d->h_stats->overflow = 0;
-    CUDA_TRY(cudaMemcpyAsync(d_sum, &d->h_stats->summary, sizeof(DecodeSummary), cudaMemcpyHostToDevice, st));
-    CUDA_TRY(cudaMemsetAsync(d_overflow, 0, 4, st));
-    d->span_begin(2);
-    first_error_kernel<<<std::min<uint32_t>((n + 255) / 256, 1024), 256, 0, st>>>(A.status, n, d_sum);
-    if (S.n_cnt > 0) {
-      uint32_t n_tiles = (n + SCAN_TILE - 1) / SCAN_TILE;
-      TRY(d->tsum.ensure(((size_t)S.n_cnt * n_tiles + S.n_cnt) * 8 + 64));
-      uint64_t* tsum = (uint64_t*)d->tsum.p;
-      uint64_t* traw = tsum + (size_t)S.n_cnt * n_tiles;
-      scan_tile_sums_kernel<<<dim3(n_tiles, S.n_cnt), SCAN_THREADS, 0, st>>>(A.cnt, n, n_tiles, tsum);
-      scan_tile_bases_kernel<<<S.n_cnt, 1024, 0, st>>>(tsum, n_tiles, traw, d_overflow);
-      scan_apply_kernel<<<dim3(n_tiles, S.n_cnt), SCAN_THREADS, 0, st>>>(A.cnt, n, n_tiles, tsum, traw, (int32_t* const*)dt_scan);
-    }
-    summary_kernel<<<1, 256, 0, st>>>(A.status, A.rec_off, n, d_sum, (const int32_t* const*)dt_scan, (uint32_t)S.n_cnt, d_totals);
-    d->span_end(S.n_cnt > 0 ? 5 : 2);
-    CUDA_TRY(cudaMemcpyAsync(&d->h_stats->summary, d_sum, sizeof(DecodeSummary), cudaMemcpyDeviceToHost, st));
-    CUDA_TRY(cudaMemcpyAsync(&d->h_stats->overflow, d_overflow, 4, cudaMemcpyDeviceToHost, st));
-    if (S.n_cnt) CUDA_TRY(cudaMemcpyAsync(totals, d_totals, (size_t)S.n_cnt * 8, cudaMemcpyDeviceToHost, st));
-    CUDA_TRY(cudaStreamSynchronize(st));                       // sync #2: totals of the variable-width columns
-    CUDA_TRY(cudaGetLastError());
-    sum = d->h_stats->summary;
-    n_eff = sum.n_eff;
-    if (sum.first_err_row != 0xffffffffu) {         // a failing record: the stream stops in front of it
-      used = sum.consumed;
-      if (consumed) *consumed = used;
-      b->info.consumed_bytes = (int64_t)used;
-    }
-    if (d->h_stats->overflow) {
-      // a prefix beyond int32 somewhere in the batch: only fatal if it is inside the delivered rows
-      for (int a = 0; a < S.n_cnt; ++a) if (totals[a] < 0 || totals[a] > 0x7fffffffLL) return fail(TFR_E_BATCH_TOO_LARGE, "Arrow int32 offsets overflow; decode smaller blocks");
-    }
-    // ---- variable-width outputs ----
-    std::vector<size_t> lvl_off((size_t)S.n_var * 3, 0), val_off(S.n_var, 0);
-    size_t var_bytes = 0;
-    for (int v = 0; v < S.n_var; ++v) {
-      const DevField& fd = S.fields[S.var_field[v]];
-      for (int l = 1; l < fd.n_levels; ++l) { lvl_off[v * 3 + l] = var_bytes; var_bytes += align_up(((size_t)totals[fd.cnt_slot + l - 1] + 1) * 4, 256); }
-      val_off[v] = var_bytes; var_bytes += align_up((size_t)totals[fd.cnt_slot + fd.n_levels - 1] * fd.width + 8, 256);
-    }
-    if (var_bytes) CUDA_TRY(cudaMallocAsync(&b->dev_var, var_bytes, st));
-    b->dev_var_bytes = var_bytes;
-    uint8_t* vx = (uint8_t*)b->dev_var;
-    for (int v = 0; v < S.n_var; ++v) {
-      const DevField& fd = S.fields[S.var_field[v]];
-      t_offs[v * 3 + 0] = fx + off0_off[v];
-      for (int l = 1; l < 3; ++l) t_offs[v * 3 + l] = l < fd.n_levels ? vx + lvl_off[v * 3 + l] : nullptr;
-      for (int l = 1; l < fd.n_levels; ++l) CUDA_TRY(cudaMemsetAsync(vx + lvl_off[v * 3 + l], 0, 4, st));
-      t_vals[v] = vx + val_off[v];
-    }
-    CUDA_TRY(cudaMemcpyAsync(dt_offs, t_offs, ((size_t)S.n_var * 4) * sizeof(void*), cudaMemcpyHostToDevice, st));
-    A.n_eff = n_eff; A.scan = (const int32_t* const*)dt_scan; A.offs = (int32_t* const*)dt_offs; A.var_values = (void* const*)dt_vals;
-    A.var_field = d->dsch.d_var_field;
-    if (n_eff > 0 && S.n_var > 0) {
-      uint32_t g2 = std::min<uint32_t>((n_eff + warps - 1) / warps, (uint32_t)d->ctx->sm_count * 16);
-      d->span_begin(3);
-      decode_pass2_kernel<<<g2, warps * 32, 0, st>>>(A);
-      d->span_end(1);
-    }
-    if (n_eff > 0 && nf > 0) {
-      uint32_t nbytes_bm = (n_eff + 7) / 8;
-      dim3 g((nbytes_bm + 255) / 256, nf);
-      g.x = std::min<uint32_t>(g.x, 4096);
-      d->span_begin(4);
-      pack_validity_kernel<<<g, 256, 0, st>>>(A.valid8, n, n_eff, nf, nb_stride, fx + bitmaps_off, b->d_null_counts);
-      d->span_end(1);
-    }
-    // device column views
-    b->cols.resize(nf);
-    int64_t out_bytes = 0;
-    for (uint32_t f = 0; f < nf; ++f) {
-      const DevField& fd = S.fields[f];
-      tfr_column c{};
-      c.elem_type = fd.elem_type; c.depth = fd.depth; c.n_levels = fd.n_levels; c.value_width = fd.width;
-      c.n_rows = n_eff; c.validity = fx + bitmaps_off + (size_t)f * nb_stride;
-      out_bytes += (n_eff + 7) / 8;
-      if (fd.fix_slot >= 0) { c.values = fx + fix_off[fd.fix_slot]; c.n_values = n_eff; out_bytes += (int64_t)n_eff * fd.width; }
-      else if (fd.var_slot >= 0) {
-        int v = fd.var_slot;
-        c.offsets[0] = (int32_t*)(fx + off0_off[v]); c.n_offsets[0] = (int64_t)n_eff + 1;
-        for (int l = 1; l < fd.n_levels; ++l) { c.offsets[l] = (int32_t*)(vx + lvl_off[v * 3 + l]); c.n_offsets[l] = totals[fd.cnt_slot + l - 1] + 1; }
-        c.values = vx + val_off[v]; c.n_values = totals[fd.cnt_slot + fd.n_levels - 1];
-        for (int l = 0; l < fd.n_levels; ++l) out_bytes += c.n_offsets[l] * 4;
-        out_bytes += c.n_values * fd.width;
+    TRY(prepare_scratch(C));
+    DecodeArgs A;
+    fill_decode_args(C, A);
+    bool done = false;
+    // ================= fast path: shared-memory tiles, one record per thread =================
+    if (d->fast_ok && nbytes / n <= 4096) {
+      const bool uniform = d->spec_state == 1;
+      TRY(d->uniform_dev.ensure(std::max<size_t>(1, S.n_var) * 4));
+      std::vector<int32_t> ul(std::max(1, S.n_var), -1);
+      std::vector<int64_t> utot(std::max(1, S.n_cnt), 0);
+      if (uniform) {
+        size_t var_bytes = 0;
+        for (int v = 0; v < S.n_var; ++v) {
+          const DevField& fd = S.fields[S.var_field[v]];
+          ul[v] = d->spec_len[v];
+          utot[fd.cnt_slot] = (int64_t)ul[v] * n;
+          if (utot[fd.cnt_slot] > 0x7fffffffLL) return fail(TFR_E_BATCH_TOO_LARGE, "Arrow int32 offsets overflow; decode smaller blocks");
+          C.t_vals[v] = (void*)var_bytes;                          // offset for now, rebased after the allocation
+          var_bytes += align_up((size_t)utot[fd.cnt_slot] * fd.width + 8, 256);
+        }
+        if (var_bytes) CUDA_TRY(cudaMallocAsync(&b->dev_var, var_bytes, st));
+        b->dev_var_bytes = var_bytes;
+        for (int v = 0; v < S.n_var; ++v) {
+          C.t_vals[v] = (uint8_t*)b->dev_var + (size_t)C.t_vals[v];
+          C.t_offs[v * 3 + 0] = C.fx + C.off0_off[v]; C.t_offs[v * 3 + 1] = nullptr; C.t_offs[v * 3 + 2] = nullptr;
+        }
+        CUDA_TRY(cudaMemcpyAsync(C.dt_offs, C.t_offs, ((size_t)S.n_var * 4) * sizeof(void*), cudaMemcpyHostToDevice, st));
       }
-      b->cols[f] = c;
+      memcpy(d->h_uniform, ul.data(), (size_t)std::max(1, S.n_var) * 4);
+      CUDA_TRY(cudaMemcpyAsync(d->uniform_dev.p, d->h_uniform, (size_t)std::max(1, S.n_var) * 4, cudaMemcpyHostToDevice, st));
+      CUDA_TRY(cudaMemsetAsync(dflags_ptr(d), 0, 4, st));
+      TileArgs TA{};
+      TA.data = C.d_data; TA.nbytes = (uint32_t)nbytes; TA.chunks = (const ChunkInfo*)d->chunks.p; TA.chunk_base = (const uint32_t*)d->chunk_base.p;
+      TA.n_chunks = C.n_chunks; TA.chunk_bytes = C.chunk_bytes; TA.n = n; TA.verify = C.verify; TA.sch = d->dsch.view; TA.tabs = d->ctx->d_tabs;
+      TA.valid8 = A.valid8; TA.fix_values = A.fix_values; TA.cnt = A.cnt; TA.src = A.src; TA.cflag = A.cflag;
+      TA.uniform_len = (const int32_t*)d->uniform_dev.p; TA.var_values = (void* const*)C.dt_vals; TA.flags = dflags_ptr(d);
+      const uint32_t smem = tile_smem_bytes(d->tile_threads, C.chunk_bytes);
+      d->span_begin(1);
+      if (d->tile_threads == 32) launch_tile<32>(TA, smem, st);
+      else if (d->tile_threads == 64) launch_tile<64>(TA, smem, st);
+      else launch_tile<128>(TA, smem, st);
+      d->span_end(1); d->pass1_launches++;
+      uint32_t tflags = 0;
+      if (uniform) {
+        if (S.n_var) {       // Arrow offsets of uniform columns: offs[i] = i * L
+          d->span_begin(2);
+          uniform_offsets_kernel<<<dim3(std::min<uint32_t>((n + 256) / 256, 512), S.n_var), 256, 0, st>>>((int32_t* const*)C.dt_offs, 3, (const int32_t*)d->uniform_dev.p, (uint32_t)S.n_var, n);
+          d->span_end(1);
+        }
+        CUDA_TRY(cudaMemcpyAsync(&d->h_stats->overflow, dovf_ptr(d), 8, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaStreamSynchronize(st));                  // the only other sync of the fast path: the verdict flag
+        CUDA_TRY(cudaGetLastError());
+        tflags = (&d->h_stats->overflow)[1];
+        if (!(tflags & TF_FALLBACK)) {
+          for (int a = 0; a < S.n_cnt; ++a) totals[a] = utot[a];
+          TRY(finish_var_and_views(C, A, n, totals, false));
+          done = true;
+        } else {
+          if (tflags & TF_SHAPE) d->spec_state = -1;          // shapes are not uniform after all: stop speculating
+          if (b->dev_var) { cudaFreeAsync(b->dev_var, st); b->dev_var = nullptr; b->dev_var_bytes = 0; }
+        }
+      } else {
+        TRY(scans_and_sync(C, A, false));
+        tflags = (&d->h_stats->overflow)[1];
+        if (!(tflags & TF_FALLBACK)) {
+          if (d->h_stats->overflow)
+            for (int a = 0; a < S.n_cnt; ++a) if (totals[a] < 0 || totals[a] > 0x7fffffffLL) return fail(TFR_E_BATCH_TOO_LARGE, "Arrow int32 offsets overflow; decode smaller blocks");
+          TRY(finish_var_and_views(C, A, n, totals, true));
+          done = true;
+          // learn shapes: every variable-width column single-level and total == n * (count of row 0)
+          if (d->spec_state == 0 && S.n_var > 0) {
+            bool ok = true;
+            for (int v = 0; v < S.n_var && ok; ++v) {
+              const DevField& fd = S.fields[S.var_field[v]];
+              int64_t c0 = totals[S.n_cnt + fd.cnt_slot];
+              if (fd.n_levels != 1 || c0 <= 0 || totals[fd.cnt_slot] != c0 * (int64_t)n) ok = false;
+              else d->spec_len[v] = (int32_t)c0;
+            }
+            d->spec_state = ok ? 1 : -1;
+          }
+        }
+      }
+      if (done) { n_eff = n; sum.n_eff = n; }
     }
-    b->info.out_bytes = out_bytes;
+    // ================= general path: warp per record, full protobuf semantics =================
+    if (!done) {
+      TRY(ensure_rec_off(C));
+      fill_decode_args(C, A);
+      const uint32_t warps = 8;
+      size_t smem1 = CRC_SMEM_WORDS * 4 + (size_t)warps * ((nf + 3) & ~3u);
+      uint32_t g1 = std::min<uint32_t>((n + warps - 1) / warps, (uint32_t)d->ctx->sm_count * 16);
+      d->span_begin(1);
+      decode_pass1_kernel<<<g1, warps * 32, smem1, st>>>(A);
+      d->span_end(1); d->pass1_launches++;
+      TRY(scans_and_sync(C, A, true));
+      sum = d->h_stats->summary;
+      n_eff = sum.n_eff;
+      if (sum.first_err_row != 0xffffffffu) used = sum.consumed;       // a failing record: the stream stops in front of it
+      if (d->h_stats->overflow)
+        for (int a = 0; a < S.n_cnt; ++a) if (totals[a] < 0 || totals[a] > 0x7fffffffLL) return fail(TFR_E_BATCH_TOO_LARGE, "Arrow int32 offsets overflow; decode smaller blocks");
+      TRY(finish_var_and_views(C, A, n_eff, totals, true));
+    }
   } else {
     // no complete record: empty columns
     b->cols.resize(nf);
@@ -624,14 +792,15 @@ extern "C" int32_t tfr_decode(tfr_decoder* d, const void* data, size_t nbytes, i
       const DevField& fd = S.fields[f];
       tfr_column c{};
       c.elem_type = fd.elem_type; c.depth = fd.depth; c.n_levels = fd.n_levels; c.value_width = fd.width;
-      c.validity = fx + bitmaps_off + (size_t)f * nb_stride;
-      if (fd.var_slot >= 0) { c.offsets[0] = (int32_t*)(fx + off0_off[fd.var_slot]); c.n_offsets[0] = 1; }
-      if (fd.fix_slot >= 0) c.values = fx + fix_off[fd.fix_slot];
-      // deeper levels of an empty column: a single zero offset, served from the level-0 array (also a single 0)
+      c.validity = C.fx + C.bitmaps_off + (size_t)f * C.nb_stride;
+      if (fd.var_slot >= 0) { c.offsets[0] = (int32_t*)(C.fx + C.off0_off[fd.var_slot]); c.n_offsets[0] = 1; }
+      if (fd.fix_slot >= 0) c.values = C.fx + C.fix_off[fd.fix_slot];
       for (int l = 1; l < fd.n_levels; ++l) { c.offsets[l] = c.offsets[0]; c.n_offsets[l] = 1; }
       b->cols[f] = c;
     }
   }
+  if (consumed) *consumed = used;
+  b->info.consumed_bytes = (int64_t)used;
   // ---- first error in record order: per-row status (pass 1) or the framing stop at row n ----
   b->info.n_rows = n_eff;
   if (n > 0 && sum.first_err_row != 0xffffffffu) {

@@ -24,6 +24,7 @@ struct CrcTables {
   uint32_t t0[256];
   uint32_t k128[4][256];
   uint32_t xw[40];
+  uint32_t s8[8][256];   // slicing-by-8 tables (tile.cuh: one record per thread, serial CRC from shared memory)
 };
 #define CRC_SMEM_WORDS (256 + 1024 + 40)
 

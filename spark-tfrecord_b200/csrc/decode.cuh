@@ -27,6 +27,7 @@ struct DecodeArgs {
   const uint8_t* data;        // framed bytes (device)
   const uint32_t* rec_off;    // [n+1]
   uint32_t n;                 // records to process
+  uint32_t nbytes;            // size of `data`
   uint32_t verify;
   DevSchema sch;
   const CrcTables* tabs;
@@ -633,7 +634,7 @@ __global__ void __launch_bounds__(256) decode_pass2_kernel(DecodeArgs A) {
           Cur pk{p, p + (size_t)cnt0 * 10};
           for (uint32_t i = 0; i < cnt0; ++i) { uint64_t x; if (!rd_varint64(pk, x)) break; sink_int(s, x); }
         } else {
-          Cur c{p, A.data + A.rec_off[row + 1]};
+          Cur c{p, A.data + A.nbytes};
           for (uint32_t i = 0; i < cnt0; ++i) {
             uint32_t tag, l;
             if (!rd_tag(c, tag) || !rd_len(c, l)) break;
@@ -690,9 +691,16 @@ __global__ void first_error_kernel(const uint32_t* __restrict__ status, uint32_t
 // n_eff + totals at n_eff for every scanned array (so that rows after the first error vanish)
 __global__ void summary_kernel(const uint32_t* __restrict__ status, const uint32_t* __restrict__ rec_off, uint32_t n,
                                DecodeSummary* __restrict__ out, const int32_t* const* __restrict__ scan, uint32_t n_cnt,
-                               int64_t* __restrict__ totals) {
+                               int64_t* __restrict__ totals, int64_t* __restrict__ first_counts) {
   uint32_t e = out->first_err_row;
   uint32_t n_eff = e == 0xffffffffu ? n : e;
-  if (threadIdx.x == 0) { out->n_eff = n_eff; out->first_err_status = e == 0xffffffffu ? 0 : status[e]; out->consumed = rec_off[n_eff]; }
-  for (uint32_t a = threadIdx.x; a < n_cnt; a += blockDim.x) totals[a] = scan[a][n_eff];
+  if (threadIdx.x == 0) {
+    out->n_eff = n_eff;
+    out->first_err_status = (e == 0xffffffffu || !status) ? 0 : status[e];
+    out->consumed = rec_off ? rec_off[n_eff] : 0;
+  }
+  for (uint32_t a = threadIdx.x; a < n_cnt; a += blockDim.x) {
+    totals[a] = scan[a][n_eff];
+    first_counts[a] = n_eff ? scan[a][1] : 0;       // count of row 0 (shape learning for the tile fast path)
+  }
 }

@@ -192,3 +192,59 @@ def test_frame_speculation_repair_paths(native, oracle):
     assert info["error_code"] == 0 and info["n_rows"] == len(pay) and used == len(data)
     assert info["frame_repairs"] > 0
     assert_columns_equal(got, want.columns, ["byteArray"], "repair")
+
+
+def test_fast_path_learns_then_speculates_then_recovers(native, oracle):
+    """tile fast path: batch 1 runs in count mode and learns the shapes, batch 2+ write uniform columns in the
+    same pass (speculation), a batch with a different shape falls back to the general path -- all bit-exact"""
+    from oracle.corpus import cfg2_columns
+    dec = native.Decoder(cfg2_columns(1, seed=1)[0])
+    try:
+        for i, (n, fl) in enumerate([(3000, 8), (3100, 8), (2900, 8), (2000, 5), (2500, 8)]):
+            sch, cols = cfg2_columns(n, seed=100 + i, float_len=fl)
+            data, rc, _ = oracle.encode(cols, sch)
+            batch, used = dec.decode(data)
+            assert batch.info["error_code"] == 0 and used == len(data)
+            assert_columns_equal(batch.to_host(), cols, sch.names, f"speculation batch {i}")
+            batch.release()
+        # ragged lengths inside one batch + nulls: never uniform
+        from oracle.corpus import mixed_columns
+    finally:
+        dec.close()
+    sch, cols = cfg2_columns(4000, seed=5)
+    # a corrupt record in the middle of a speculating decoder: error semantics must still be exact
+    data, rc, _ = oracle.encode(cols, sch)
+    dec = native.Decoder(sch)
+    try:
+        for _ in range(2):
+            b, _ = dec.decode(data); b.release()
+        bad = bytearray(data); bad[len(data) // 3] ^= 0x20
+        want = oracle.decode(bytes(bad), sch)
+        b, used = dec.decode(bytes(bad))
+        assert b.info["error_code"] == want.info["error_code"] != 0
+        assert b.info["error_row"] == want.info["error_row"] and used == want.info["consumed_bytes"]
+        assert_columns_equal(b.to_host(), want.columns, sch.names, "error under speculation")
+        b.release()
+        b, used = dec.decode(data)
+        assert b.info["error_code"] == 0
+        assert_columns_equal(b.to_host(), cols, sch.names, "after error")
+        b.release()
+    finally:
+        dec.close()
+
+
+@pytest.mark.parametrize("env", [{"TFR_DISABLE_FAST": "1"}, {"TFR_TILE_KB": "32", "TFR_TILE_THREADS": "64"}, {"TFR_TILE_KB": "96", "TFR_TILE_THREADS": "128"}])
+def test_path_variants_agree(native, oracle, env, monkeypatch):
+    """general path only / other tile geometries: same bits"""
+    from oracle.corpus import cfg2_columns, mixed_columns
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    for sch, cols in (cfg2_columns(6000, seed=77), mixed_columns(3000, seed=78)):
+        data, rc, _ = oracle.encode(cols, sch)
+        dec = native.Decoder(sch)
+        for _ in range(3):
+            b, used = dec.decode(data)
+            assert b.info["error_code"] == 0 and used == len(data)
+            assert_columns_equal(b.to_host(), cols, sch.names, str(env))
+            b.release()
+        dec.close()
