@@ -71,6 +71,7 @@ struct DeviceCtx {
   CrcTables* d_tabs = nullptr;
   cudaError_t err = cudaSuccess;
   int sm_count = 148;
+  int max_smem_optin = 48 * 1024;
 };
 static DeviceCtx g_ctx[64];
 
@@ -119,6 +120,14 @@ static int32_t get_ctx(int device, DeviceCtx** out) {
     c.err = cudaGetDeviceProperties(&prop, device);
     if (c.err != cudaSuccess) return;
     c.sm_count = prop.multiProcessorCount;
+    c.max_smem_optin = (int)prop.sharedMemPerBlockOptin;
+    {   // keep stream-ordered allocations cached in the pool instead of returning them to the OS at every sync
+      cudaMemPool_t pool;
+      if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+        unsigned long long thr = ~0ull;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+      }
+    }
     CrcTables* h = new CrcTables;
     build_crc_tables(*h);
     c.err = cudaMalloc(&c.d_tabs, sizeof(CrcTables));
@@ -269,7 +278,7 @@ struct tfr_decoder {
   PinnedPool host_pool;
   // fast path (tile.cuh)
   bool fast_ok = false;
-  uint32_t tile_bytes = 49152, tile_threads = 32;
+  size_t tile_smem_set = 0;
   int spec_state = 0;                   // 0 learning, 1 speculating on uniform shapes, -1 disabled
   std::vector<int32_t> spec_len;
   DevBuf uniform_dev;
@@ -331,8 +340,6 @@ extern "C" int32_t tfr_decoder_create(const tfr_schema* schema, int32_t device, 
     bool ok = d->schema.record_type == TFR_RT_EXAMPLE && d->schema.fields.size() <= 128 && !getenv("TFR_DISABLE_FAST");
     for (const DevField& f : d->schema.fields) if (f.depth > 1) ok = false;
     d->fast_ok = ok;
-    if (const char* e = getenv("TFR_TILE_KB")) { int kb = atoi(e); if (kb >= 16 && kb <= 192) d->tile_bytes = (uint32_t)kb * 1024; }
-    if (const char* e = getenv("TFR_TILE_THREADS")) { int t = atoi(e); if (t == 32 || t == 64 || t == 128) d->tile_threads = (uint32_t)t; }
     if (getenv("TFR_DISABLE_SPECULATION")) d->spec_state = -1;
     d->spec_len.assign(std::max(1, d->schema.n_var), -1);
     CUDA_TRY(cudaHostAlloc((void**)&d->h_uniform, std::max<size_t>(1, d->schema.n_var) * 4, cudaHostAllocDefault));
@@ -544,7 +551,7 @@ static int32_t scans_and_sync(DecodeCtx& C, DecodeArgs& A, bool with_status) {
 }
 
 // variable-width outputs sized from totals, pass 2, validity pack, column views
-static int32_t finish_var_and_views(DecodeCtx& C, DecodeArgs& A, uint32_t n_eff, const int64_t* totals, bool run_pass2) {
+static int32_t finish_var_and_views(DecodeCtx& C, DecodeArgs& A, uint32_t n_eff, const int64_t* totals, bool run_pass2, bool pack = true) {
   tfr_decoder* d = C.d; const tfr_schema& S = d->schema; tfr_batch* b = C.b; cudaStream_t st = C.st; const uint32_t n = C.n, nf = C.nf;
   std::vector<size_t> lvl_off((size_t)S.n_var * 3, 0), val_off(S.n_var, 0);
   uint8_t* vx = (uint8_t*)b->dev_var;
@@ -579,7 +586,7 @@ static int32_t finish_var_and_views(DecodeCtx& C, DecodeArgs& A, uint32_t n_eff,
     size_t off = 0;
     for (int v = 0; v < S.n_var; ++v) { val_off[v] = off; off += align_up((size_t)totals[S.fields[S.var_field[v]].cnt_slot] * S.fields[S.var_field[v]].width + 8, 256); }
   }
-  if (n_eff > 0 && nf > 0) {
+  if (pack && n_eff > 0 && nf > 0) {
     uint32_t nbytes_bm = (n_eff + 7) / 8;
     dim3 g((nbytes_bm + 255) / 256, nf);
     g.x = std::min<uint32_t>(g.x, 4096);
@@ -608,12 +615,6 @@ static int32_t finish_var_and_views(DecodeCtx& C, DecodeArgs& A, uint32_t n_eff,
   }
   b->info.out_bytes = out_bytes;
   return TFR_OK;
-}
-
-template <int T>
-static void launch_tile(const TileArgs& TA, uint32_t smem, cudaStream_t st) {
-  cudaFuncSetAttribute(decode_tile_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  decode_tile_kernel<T><<<TA.n_chunks, T, smem, st>>>(TA);
 }
 
 extern "C" int32_t tfr_decode(tfr_decoder* d, const void* data, size_t nbytes, int32_t data_on_device, int32_t is_final, tfr_batch** out,
@@ -646,7 +647,7 @@ extern "C" int32_t tfr_decode(tfr_decoder* d, const void* data, size_t nbytes, i
   FrameResult fr{};
   fr.stop = FS_EOF;
   if (nbytes) {
-    C.chunk_bytes = d->fast_ok ? d->tile_bytes : pick_chunk_bytes(nbytes, d->ctx->sm_count);
+    C.chunk_bytes = pick_chunk_bytes(nbytes, d->ctx->sm_count);
     C.n_chunks = (uint32_t)((nbytes + C.chunk_bytes - 1) / C.chunk_bytes);
     TRY(d->chunks.ensure((size_t)C.n_chunks * sizeof(ChunkInfo)));
     TRY(d->chunk_base.ensure(((size_t)C.n_chunks + 1) * sizeof(uint32_t)));
@@ -656,7 +657,7 @@ extern "C" int32_t tfr_decode(tfr_decoder* d, const void* data, size_t nbytes, i
     CUDA_TRY(cudaMemcpyAsync(d_fr, &d->h_stats->frame, sizeof(FrameResult), cudaMemcpyHostToDevice, st));
     uint32_t grid = std::min<uint32_t>((C.n_chunks + 7) / 8, (uint32_t)d->ctx->sm_count * 8);
     d->span_begin(0);
-    frame_scan_kernel<<<grid, 256, 0, st>>>(C.d_data, (uint32_t)nbytes, C.chunk_bytes, C.n_chunks, C.verify, d->ctx->d_tabs, (ChunkInfo*)d->chunks.p);
+    frame_scan_kernel<<<grid, 256, 0, st>>>(C.d_data, (uint32_t)nbytes, C.chunk_bytes, C.n_chunks, C.verify, d->ctx->d_tabs, (ChunkInfo*)d->chunks.p, d_fr);
     frame_check_kernel<<<(C.n_chunks + 255) / 256, 256, 0, st>>>((const ChunkInfo*)d->chunks.p, C.n_chunks, d_fr);
     frame_repair_kernel<<<1, 32, 0, st>>>(C.d_data, (uint32_t)nbytes, C.chunk_bytes, C.n_chunks, C.verify, d->ctx->d_tabs, (ChunkInfo*)d->chunks.p, d_fr);
     frame_finish_kernel<<<1, 1024, 0, st>>>((const ChunkInfo*)d->chunks.p, C.n_chunks, (uint32_t)nbytes, (uint32_t*)d->chunk_base.p, d_fr);
@@ -688,8 +689,13 @@ extern "C" int32_t tfr_decode(tfr_decoder* d, const void* data, size_t nbytes, i
     fill_decode_args(C, A);
     bool done = false;
     // ================= fast path: shared-memory tiles, one record per thread =================
-    if (d->fast_ok && nbytes / n <= 4096) {
+    const uint32_t names_bytes = (uint32_t)S.names.size();
+    const uint32_t tile_cap = (uint32_t)align_up((size_t)TILE_ROWS * ((size_t)fr.max_len + 16) + 32, 128);
+    const size_t tile_smem = tile_smem_bytes(nf, names_bytes, tile_cap);
+    if (d->fast_ok && tile_smem <= (size_t)d->ctx->max_smem_optin) {
       const bool uniform = d->spec_state == 1;
+      TRY(ensure_rec_off(C));
+      fill_decode_args(C, A);
       TRY(d->uniform_dev.ensure(std::max<size_t>(1, S.n_var) * 4));
       std::vector<int32_t> ul(std::max(1, S.n_var), -1);
       std::vector<int64_t> utot(std::max(1, S.n_cnt), 0);
@@ -715,15 +721,17 @@ extern "C" int32_t tfr_decode(tfr_decoder* d, const void* data, size_t nbytes, i
       CUDA_TRY(cudaMemcpyAsync(d->uniform_dev.p, d->h_uniform, (size_t)std::max(1, S.n_var) * 4, cudaMemcpyHostToDevice, st));
       CUDA_TRY(cudaMemsetAsync(dflags_ptr(d), 0, 4, st));
       TileArgs TA{};
-      TA.data = C.d_data; TA.nbytes = (uint32_t)nbytes; TA.chunks = (const ChunkInfo*)d->chunks.p; TA.chunk_base = (const uint32_t*)d->chunk_base.p;
-      TA.n_chunks = C.n_chunks; TA.chunk_bytes = C.chunk_bytes; TA.n = n; TA.verify = C.verify; TA.sch = d->dsch.view; TA.tabs = d->ctx->d_tabs;
-      TA.valid8 = A.valid8; TA.fix_values = A.fix_values; TA.cnt = A.cnt; TA.src = A.src; TA.cflag = A.cflag;
+      TA.data = C.d_data; TA.nbytes = (uint32_t)nbytes; TA.rec_off = (const uint32_t*)d->rec_off.p; TA.n = n; TA.tile_cap = tile_cap;
+      TA.verify = C.verify; TA.names_bytes = names_bytes; TA.sch = d->dsch.view; TA.tabs = d->ctx->d_tabs;
+      TA.bitmaps = C.fx + C.bitmaps_off; TA.nb_stride = C.nb_stride; TA.null_counts = b->d_null_counts;
+      TA.fix_values = A.fix_values; TA.cnt = A.cnt; TA.src = A.src; TA.cflag = A.cflag;
       TA.uniform_len = (const int32_t*)d->uniform_dev.p; TA.var_values = (void* const*)C.dt_vals; TA.flags = dflags_ptr(d);
-      const uint32_t smem = tile_smem_bytes(d->tile_threads, C.chunk_bytes);
+      if (d->tile_smem_set < tile_smem) {
+        CUDA_TRY(cudaFuncSetAttribute(decode_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_smem));
+        d->tile_smem_set = tile_smem;
+      }
       d->span_begin(1);
-      if (d->tile_threads == 32) launch_tile<32>(TA, smem, st);
-      else if (d->tile_threads == 64) launch_tile<64>(TA, smem, st);
-      else launch_tile<128>(TA, smem, st);
+      decode_tile_kernel<<<(n + TILE_ROWS - 1) / TILE_ROWS, 64, tile_smem, st>>>(TA);
       d->span_end(1); d->pass1_launches++;
       uint32_t tflags = 0;
       if (uniform) {
@@ -738,7 +746,7 @@ extern "C" int32_t tfr_decode(tfr_decoder* d, const void* data, size_t nbytes, i
         tflags = (&d->h_stats->overflow)[1];
         if (!(tflags & TF_FALLBACK)) {
           for (int a = 0; a < S.n_cnt; ++a) totals[a] = utot[a];
-          TRY(finish_var_and_views(C, A, n, totals, false));
+          TRY(finish_var_and_views(C, A, n, totals, false, false));
           done = true;
         } else {
           if (tflags & TF_SHAPE) d->spec_state = -1;          // shapes are not uniform after all: stop speculating
@@ -750,7 +758,7 @@ extern "C" int32_t tfr_decode(tfr_decoder* d, const void* data, size_t nbytes, i
         if (!(tflags & TF_FALLBACK)) {
           if (d->h_stats->overflow)
             for (int a = 0; a < S.n_cnt; ++a) if (totals[a] < 0 || totals[a] > 0x7fffffffLL) return fail(TFR_E_BATCH_TOO_LARGE, "Arrow int32 offsets overflow; decode smaller blocks");
-          TRY(finish_var_and_views(C, A, n, totals, true));
+          TRY(finish_var_and_views(C, A, n, totals, true, false));
           done = true;
           // learn shapes: every variable-width column single-level and total == n * (count of row 0)
           if (d->spec_state == 0 && S.n_var > 0) {
@@ -769,6 +777,8 @@ extern "C" int32_t tfr_decode(tfr_decoder* d, const void* data, size_t nbytes, i
     }
     // ================= general path: warp per record, full protobuf semantics =================
     if (!done) {
+      // (a failed fast attempt may have touched the null counters)
+      CUDA_TRY(cudaMemsetAsync(b->d_null_counts, 0, sizeof(unsigned long long) * std::max<uint32_t>(nf, 1), st));
       TRY(ensure_rec_off(C));
       fill_decode_args(C, A);
       const uint32_t warps = 8;

@@ -569,12 +569,12 @@ __global__ void __launch_bounds__(256) decode_pass2_kernel(DecodeArgs A) {
     }
     for (uint32_t v = lane; v < nvar; v += 32) {
       const int f = A.var_field[v];
-      if (!A.valid8[(size_t)f * A.n + row]) continue;
       const DevField& fd = A.sch.fields[f];
-      const uint32_t src = A.src[(size_t)v * A.n + row];
-      const uint32_t flag = A.cflag[(size_t)v * A.n + row];
       const int32_t off0 = A.scan[fd.cnt_slot][row];
       const uint32_t cnt0 = (uint32_t)(A.scan[fd.cnt_slot][row + 1] - off0);
+      if (cnt0 == 0) continue;             // null, empty list or empty string: nothing to emit (src/cflag are undefined for nulls)
+      const uint32_t src = A.src[(size_t)v * A.n + row];
+      const uint32_t flag = A.cflag[(size_t)v * A.n + row];
       ElemSink s;
       s.elem_type = fd.elem_type; s.values = reinterpret_cast<uint8_t*>(A.var_values[v]);
       s.leaf_off = nullptr; s.epos = 0; s.limit = 0xffffffffu; s.taken = 0;

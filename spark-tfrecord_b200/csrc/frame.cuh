@@ -44,12 +44,13 @@ struct FrameResult {       // written by the device, read back by the host (one 
   uint32_t stop_pos;       // byte offset of the record (or fragment) that stopped the scan
   uint32_t repairs;        // chunks re-chained by frame_repair
   uint32_t first_bad;      // first chunk whose link check failed, 0xffffffff if none
-  uint32_t pad[3];
+  uint32_t max_len;        // upper bound of the payload length of any record (sizes the shared-memory tiles)
+  uint32_t pad[2];
 };
 
 // walk headers starting at q until the chain leaves [.., ce) or stops; returns stop code
 __device__ __forceinline__ uint32_t frame_chain(const uint32_t* t0, const uint8_t* data, uint32_t nbytes, uint32_t ce,
-                                                bool verify, uint32_t& q, uint32_t& count) {
+                                                bool verify, uint32_t& q, uint32_t& count, uint32_t& max_len) {
   while (q < ce) {
     uint32_t left = nbytes - q;
     if (left < 8) return FS_STRAY;
@@ -62,6 +63,7 @@ __device__ __forceinline__ uint32_t frame_chain(const uint32_t* t0, const uint8_
     if (hi != 0 || lo > 0x7fffffffu) return FS_TOO_LARGE;
     if ((uint64_t)left < 16ull + lo) return FS_PART_REC;
     q += 16 + lo;
+    max_len = max(max_len, lo);
     ++count;
   }
   return q == nbytes ? FS_EOF : FS_LEFT;
@@ -70,7 +72,7 @@ __device__ __forceinline__ uint32_t frame_chain(const uint32_t* t0, const uint8_
 // one warp per chunk
 __global__ void __launch_bounds__(256) frame_scan_kernel(const uint8_t* __restrict__ data, uint32_t nbytes, uint32_t chunk_bytes,
                                                          uint32_t n_chunks, uint32_t verify, const CrcTables* __restrict__ tabs,
-                                                         ChunkInfo* __restrict__ chunks) {
+                                                         ChunkInfo* __restrict__ chunks, FrameResult* __restrict__ res) {
   __shared__ uint32_t t0[256];
   for (int i = threadIdx.x; i < 256; i += blockDim.x) t0[i] = tabs->t0[i];
   __syncthreads();
@@ -99,9 +101,10 @@ __global__ void __launch_bounds__(256) frame_scan_kernel(const uint8_t* __restri
     ChunkInfo ci;
     ci.first = first; ci.end = first; ci.count = 0; ci.stop = FS_NONE;
     if (first != 0xffffffffu) {
-      uint32_t q = first, cnt = 0;
-      ci.stop = frame_chain(t0, data, nbytes, ce, verify != 0, q, cnt);   // uniform across the warp
+      uint32_t q = first, cnt = 0, mx = 0;
+      ci.stop = frame_chain(t0, data, nbytes, ce, verify != 0, q, cnt, mx);   // uniform across the warp
       ci.end = q; ci.count = cnt;
+      if (lane == 0 && mx) atomicMax(&res->max_len, mx);                  // a false candidate can only enlarge the bound
     }
     if (lane == 0) chunks[k] = ci;
   }
@@ -148,9 +151,10 @@ __global__ void frame_repair_kernel(const uint8_t* __restrict__ data, uint32_t n
       // fast-forward over consistent chunks
       continue;
     }
-    uint32_t q = F, cnt = 0;
+    uint32_t q = F, cnt = 0, mx = 0;
     ci.first = F;
-    ci.stop = frame_chain(t0, data, nbytes, ce, verify != 0, q, cnt);
+    ci.stop = frame_chain(t0, data, nbytes, ce, verify != 0, q, cnt, mx);
+    if (mx) atomicMax(&res->max_len, mx);
     ci.end = q; ci.count = cnt;
     chunks[k] = ci; ++repairs;
     if (ci.stop != FS_LEFT) stopped = true; else F = q;
