@@ -228,6 +228,7 @@ extern "C" int32_t tfr_schema_num_fields(const tfr_schema* s) { return s ? (int3
 // device copy of a schema
 struct DevSchemaBuf {
   DevField* d_fields = nullptr; uint8_t* d_names = nullptr; int32_t* d_ht = nullptr; int32_t* d_var_field = nullptr;
+  FieldTemplate* d_templates = nullptr;
   DevSchema view{};
   int32_t upload(const tfr_schema& s) {
     size_t nf = s.fields.size();
@@ -239,12 +240,34 @@ struct DevSchemaBuf {
     if (!s.names.empty()) CUDA_TRY(cudaMemcpy(d_names, s.names.data(), s.names.size(), cudaMemcpyHostToDevice));
     CUDA_TRY(cudaMemcpy(d_ht, s.ht.data(), s.ht.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
     if (!s.var_field.empty()) CUDA_TRY(cudaMemcpy(d_var_field, s.var_field.data(), s.var_field.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+    {
+      // canonical entry prefix of every field: 0A ? 0A klen key 12 ? kindtag ?   (? = length bytes, masked out)
+      std::vector<FieldTemplate> tp(std::max<size_t>(1, nf));
+      for (size_t f = 0; f < nf; ++f) {
+        FieldTemplate& t = tp[f];
+        memset(&t, 0, sizeof t);
+        const DevField& fd = s.fields[f];
+        t.kind = (uint32_t)fd.kind;
+        const uint32_t klen = fd.name_len, total = klen + 8;
+        if (fd.kind == K_NONE || klen >= 0x80 || total > TILE_TPL_WORDS * 4) continue;      // no template: generic parse
+        uint8_t bytes[TILE_TPL_WORDS * 4] = {0}, mask[TILE_TPL_WORDS * 4] = {0};
+        auto put = [&](uint32_t i, uint8_t b, bool fixed) { bytes[i] = b; mask[i] = fixed ? 0xFF : 0x00; };
+        put(0, 0x0A, true); put(1, 0, false); put(2, 0x0A, true); put(3, (uint8_t)klen, true);
+        for (uint32_t i = 0; i < klen; ++i) put(4 + i, s.names[fd.name_off + i], true);
+        put(4 + klen, 0x12, true); put(5 + klen, 0, false);
+        put(6 + klen, fd.kind == K_BYTES ? 0x0A : fd.kind == K_FLOAT ? 0x12 : 0x1A, true); put(7 + klen, 0, false);
+        t.n_words = (total + 3) / 4;
+        memcpy(t.words, bytes, sizeof bytes); memcpy(t.mask, mask, sizeof mask);
+      }
+      CUDA_TRY(cudaMalloc(&d_templates, tp.size() * sizeof(FieldTemplate)));
+      CUDA_TRY(cudaMemcpy(d_templates, tp.data(), tp.size() * sizeof(FieldTemplate), cudaMemcpyHostToDevice));
+    }
     view.n_fields = (int32_t)nf; view.record_type = s.record_type; view.ht_mask = (int32_t)s.ht.size() - 1;
     view.n_fix = s.n_fix; view.n_var = s.n_var; view.n_cnt = s.n_cnt;
     view.fields = d_fields; view.names = d_names; view.ht = d_ht;
     return TFR_OK;
   }
-  void free_all() { cudaFree(d_fields); cudaFree(d_names); cudaFree(d_ht); cudaFree(d_var_field); }
+  void free_all() { cudaFree(d_fields); cudaFree(d_names); cudaFree(d_ht); cudaFree(d_var_field); cudaFree(d_templates); }
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -722,7 +745,7 @@ extern "C" int32_t tfr_decode(tfr_decoder* d, const void* data, size_t nbytes, i
       CUDA_TRY(cudaMemsetAsync(dflags_ptr(d), 0, 4, st));
       TileArgs TA{};
       TA.data = C.d_data; TA.nbytes = (uint32_t)nbytes; TA.rec_off = (const uint32_t*)d->rec_off.p; TA.n = n; TA.tile_cap = tile_cap;
-      TA.verify = C.verify; TA.names_bytes = names_bytes; TA.sch = d->dsch.view; TA.tabs = d->ctx->d_tabs;
+      TA.verify = C.verify; TA.names_bytes = names_bytes; TA.sch = d->dsch.view; TA.templates = d->dsch.d_templates; TA.tabs = d->ctx->d_tabs;
       TA.bitmaps = C.fx + C.bitmaps_off; TA.nb_stride = C.nb_stride; TA.null_counts = b->d_null_counts;
       TA.fix_values = A.fix_values; TA.cnt = A.cnt; TA.src = A.src; TA.cflag = A.cflag;
       TA.uniform_len = (const int32_t*)d->uniform_dev.p; TA.var_values = (void* const*)C.dt_vals; TA.flags = dflags_ptr(d);
@@ -731,7 +754,7 @@ extern "C" int32_t tfr_decode(tfr_decoder* d, const void* data, size_t nbytes, i
         d->tile_smem_set = tile_smem;
       }
       d->span_begin(1);
-      decode_tile_kernel<<<(n + TILE_ROWS - 1) / TILE_ROWS, 64, tile_smem, st>>>(TA);
+      decode_tile_kernel<<<(n + TILE_ROWS - 1) / TILE_ROWS, TILE_THREADS, tile_smem, st>>>(TA);
       d->span_end(1); d->pass1_launches++;
       uint32_t tflags = 0;
       if (uniform) {

@@ -11,14 +11,18 @@
 // raise a flag; the host then re-runs the batch through the general kernels of decode.cuh, which
 // implement the full semantics.  So the fast path never changes a result, it only skips work.
 //
-// Mapping: one CTA = one tile = 32 consecutive records (rows 32t .. 32t+31, contiguous in memory), 2 warps.
+// Mapping: one CTA = one tile = 32 consecutive records (rows 32t .. 32t+31, contiguous in memory),
+// TILE_PARSE_WARPS parse warps + 1 CRC warp, all working on the same staged bytes.
 //   1. one thread arms an mbarrier and issues cp.async.bulk (TMA bulk copy, SASS UBLKCP) of the tile's
 //      byte range into shared memory; meanwhile all threads stage the slicing-by-8 CRC tables and the
 //      schema (field table + names) into shared memory.
-//   2. role split over the same staged bytes: warp 1 computes the masked CRC-32C of record `lane`
-//      (serial slicing-by-8, 8 bytes per step), warp 0 parses record `lane` (strict wire parse, "expected
-//      next field" key match with a hash fallback, coercions).  Two independent dependent-chains per
-//      record instead of one doubles the warps that shared-memory capacity allows per SM.
+//   2. role split over the same staged bytes: the last warp computes the masked CRC-32C of record `lane`
+//      (serial slicing-by-8, 8 bytes per step); parse warp w owns the map entries with index = w mod W of
+//      record `lane`: it fully parses those and only hops over the others (`0A elen` -> p += elen).  An
+//      owned entry is first matched against a per-field TEMPLATE of its constant bytes
+//      (0A ? 0A klen key 12 ? kind ?: a few masked word compares); only when that fails is it parsed
+//      byte by byte (hash lookup of the key, full checks).  Shared-memory capacity limits how many
+//      records an SM can stage, so more dependent-chains per staged record = more warps to hide latency.
 //   3. lane = row, rows are 32-aligned: every column store of the warp covers 32 consecutive rows
 //      (coalesced by construction, no transpose) and validity bitmaps are one __ballot_sync per field.
 //   4. variable-width columns either write element counts + source offsets (scan + decode_pass2_kernel
@@ -30,6 +34,17 @@
 #include "decode.cuh"
 
 #define TILE_ROWS 32
+#define TILE_PARSE_WARPS 4
+#define TILE_THREADS ((TILE_PARSE_WARPS + 1) * 32)
+#define TILE_TPL_WORDS 5          // template covers up to 20 bytes: key names up to 12 bytes
+
+// constant bytes of a canonical map entry of one schema field, for masked word compares
+struct FieldTemplate {
+  uint32_t words[TILE_TPL_WORDS];
+  uint32_t mask[TILE_TPL_WORDS];
+  uint32_t n_words;             // 0: no template (long name): generic parse
+  uint32_t kind;                // K_*
+};
 
 struct TileArgs {
   const uint8_t* data;
@@ -40,6 +55,7 @@ struct TileArgs {
   uint32_t verify;
   uint32_t names_bytes;
   DevSchema sch;
+  const FieldTemplate* templates;   // [n_fields]
   const CrcTables* tabs;
   uint8_t* bitmaps;             // [nf][nb_stride] Arrow validity bitmaps, written directly
   uint32_t nb_stride;
@@ -127,23 +143,27 @@ __device__ __forceinline__ uint32_t crc_serial_s8(const uint32_t* s8, const uint
 }
 
 // shared memory layout (dynamic), all sections 16-byte aligned:
-//   [0,16) mbarrier | CRC tables 8 KiB | DevField[nf] | names | tile bytes (tile_cap)
+//   [0,16) mbarrier | CRC tables 8 KiB | seen masks [W][32][2] u64 | DevField[nf] | FieldTemplate[nf] | names | tile bytes
+#define TILE_SEEN_BYTES (TILE_PARSE_WARPS * 32 * 16)
 __host__ __device__ inline uint32_t tile_schema_smem(uint32_t nf, uint32_t names_bytes) {
-  return ((nf * (uint32_t)sizeof(DevField) + 15u) & ~15u) + ((names_bytes + 15u) & ~15u);
+  return ((nf * (uint32_t)sizeof(DevField) + 15u) & ~15u) + ((nf * (uint32_t)sizeof(FieldTemplate) + 15u) & ~15u) + ((names_bytes + 15u) & ~15u);
 }
 __host__ __device__ inline uint32_t tile_smem_bytes(uint32_t nf, uint32_t names_bytes, uint32_t tile_cap) {
-  return 16 + 8192 + tile_schema_smem(nf, names_bytes) + tile_cap + 16;
+  return 16 + 8192 + TILE_SEEN_BYTES + tile_schema_smem(nf, names_bytes) + tile_cap + 64;   // +64: template compares may look a few bytes past the tile
 }
 
-__global__ void __launch_bounds__(64) decode_tile_kernel(TileArgs A) {
+__global__ void __launch_bounds__(TILE_THREADS) decode_tile_kernel(TileArgs A) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
   uint32_t* s8 = reinterpret_cast<uint32_t*>(smem_raw + 16);                               // 8 KiB
+  unsigned long long* sseen = reinterpret_cast<unsigned long long*>(smem_raw + 16 + 8192);
   const uint32_t nf = (uint32_t)A.sch.n_fields;
-  DevField* sfields = reinterpret_cast<DevField*>(smem_raw + 16 + 8192);
-  uint8_t* snames = smem_raw + 16 + 8192 + ((nf * (uint32_t)sizeof(DevField) + 15u) & ~15u);
-  uint8_t* tile_b = smem_raw + 16 + 8192 + tile_schema_smem(nf, A.names_bytes);
-  const uint32_t lane = threadIdx.x & 31, role = threadIdx.x >> 5;                         // role 0 = parse, 1 = CRC
+  uint8_t* sbase = smem_raw + 16 + 8192 + TILE_SEEN_BYTES;
+  DevField* sfields = reinterpret_cast<DevField*>(sbase);
+  FieldTemplate* stpl = reinterpret_cast<FieldTemplate*>(sbase + ((nf * (uint32_t)sizeof(DevField) + 15u) & ~15u));
+  uint8_t* snames = sbase + ((nf * (uint32_t)sizeof(DevField) + 15u) & ~15u) + ((nf * (uint32_t)sizeof(FieldTemplate) + 15u) & ~15u);
+  uint8_t* tile_b = sbase + tile_schema_smem(nf, A.names_bytes);
+  const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;                          // warps 0..W-1 parse, warp W = CRC
 
   const uint32_t row0 = blockIdx.x * TILE_ROWS;
   const uint32_t rows = min((uint32_t)TILE_ROWS, A.n - row0);
@@ -171,11 +191,14 @@ __global__ void __launch_bounds__(64) decode_tile_kernel(TileArgs A) {
   }
   {   // meanwhile: CRC tables + schema into shared memory
     const uint32_t* g = reinterpret_cast<const uint32_t*>(A.tabs->s8);
-    for (uint32_t i = threadIdx.x; i < 2048; i += 64) s8[i] = g[i];
+    for (uint32_t i = threadIdx.x; i < 2048; i += TILE_THREADS) s8[i] = g[i];
     const uint32_t* gf = reinterpret_cast<const uint32_t*>(A.sch.fields);
     uint32_t* sf = reinterpret_cast<uint32_t*>(sfields);
-    for (uint32_t i = threadIdx.x; i < nf * (uint32_t)(sizeof(DevField) / 4); i += 64) sf[i] = gf[i];
-    for (uint32_t i = threadIdx.x; i < A.names_bytes; i += 64) snames[i] = A.sch.names[i];
+    for (uint32_t i = threadIdx.x; i < nf * (uint32_t)(sizeof(DevField) / 4); i += TILE_THREADS) sf[i] = gf[i];
+    const uint32_t* gt = reinterpret_cast<const uint32_t*>(A.templates);
+    uint32_t* stw = reinterpret_cast<uint32_t*>(stpl);
+    for (uint32_t i = threadIdx.x; i < nf * (uint32_t)(sizeof(FieldTemplate) / 4); i += TILE_THREADS) stw[i] = gt[i];
+    for (uint32_t i = threadIdx.x; i < A.names_bytes; i += TILE_THREADS) snames[i] = A.sch.names[i];
   }
   __syncthreads();
   mbar_wait(bar, 0);
@@ -188,8 +211,8 @@ __global__ void __launch_bounds__(64) decode_tile_kernel(TileArgs A) {
   const uint32_t end = pay + len;
   Tile T{tile_b};
 
-  // =============================== role 1: CRC ===============================
-  if (role == 1) {
+  // =============================== last warp: CRC ===============================
+  if (wid == TILE_PARSE_WARPS) {
     if (active && A.verify) {
       uint32_t crc = crc_serial_s8(s8, tile_b, pay, len);
       if (crc_mask(crc) != t_u32(T, end)) atomicOr(A.flags, TF_FALLBACK);      // the general path reports CRC_DATA at the right record
@@ -197,8 +220,9 @@ __global__ void __launch_bounds__(64) decode_tile_kernel(TileArgs A) {
     return;
   }
 
-  // =============================== role 0: parse ===============================
+  // =============================== warps 0..W-1: parse ===============================
   bool bad = false;
+  uint32_t entry_idx = 0;
   uint32_t shape_bad = 0;
   unsigned long long seen_lo = 0, seen_hi = 0;
   if (active) {
@@ -206,34 +230,52 @@ __global__ void __launch_bounds__(64) decode_tile_kernel(TileArgs A) {
     // Example { features = 1 }: exactly one field spanning the payload
     if (len < 2 || T.b[p] != 0x0A) bad = true;
     else { ++p; if (!t_len(T, p, end, L) || p + L != end) bad = true; }
-    uint32_t next_f = 0;
+    uint32_t next_f = wid;                 // in-order data: this warp's k-th owned entry is field wid + k*W
     while (!bad && p < end) {
-      // ---- map entry: 0A elen 0A klen key 12 vlen ----
-      uint32_t elen, klen, vlen;
-      if (T.b[p] != 0x0A) { bad = true; break; }
-      ++p;
-      if (!t_len(T, p, end, elen) || end - p < elen) { bad = true; break; }
-      const uint32_t eend = p + elen;
-      if (p >= eend || T.b[p] != 0x0A) { bad = true; break; }
-      ++p;
-      if (!t_len(T, p, eend, klen) || eend - p < klen) { bad = true; break; }
-      const uint32_t key = p;
-      p += klen;
-      if (p >= eend || T.b[p] != 0x12) { bad = true; break; }
-      ++p;
-      if (!t_len(T, p, eend, vlen) || p + vlen != eend) { bad = true; break; }
-      // ---- which schema field? entries normally arrive in schema order ----
+      if (entry_idx++ % TILE_PARSE_WARPS != wid) {
+        // not ours: hop.  The owner validates the entry; here only stay inside the record.
+        uint32_t b1 = end - p >= 2 ? T.b[p + 1] : 0x80;
+        if (b1 < 0x80) p += 2 + b1;
+        else { ++p; uint32_t el; if (!t_len(T, p, end, el)) { bad = true; break; } p += el; }
+        if (p > end) { bad = true; break; }
+        continue;
+      }
+      // ---- owned entry: try the expected field's template first ----
+      uint32_t eend, vlen;
       int f = -1;
-      uint32_t hi = 0;
-      if (next_f < nf && sfields[next_f].name_len == klen) {
-        const uint8_t* nm = snames + sfields[next_f].name_off;
+      bool located = false;
+      if (next_f < nf && stpl[next_f].n_words) {
+        const FieldTemplate& tp = stpl[next_f];
+        const uint32_t klen = sfields[next_f].name_len;
         uint32_t diff = 0;
-        for (uint32_t i = 0; i < klen; ++i) { uint32_t kb = T.b[key + i]; diff |= kb ^ nm[i]; hi |= kb; }
-        if (diff == 0) f = (int)next_f;
-      } else for (uint32_t i = 0; i < klen; ++i) hi |= T.b[key + i];
-      if (hi >= 0x80 && !utf8_valid(T.b + key, klen)) { bad = true; break; }   // malformed key: the general path reports it
-      if (f < 0) {
-        // out of order / not in the schema: hash lookup over the shared-memory copy of the schema
+#pragma unroll
+        for (int w = 0; w < TILE_TPL_WORDS; ++w)
+          if ((uint32_t)w < tp.n_words) diff |= (t_u32(T, p + 4 * w) ^ tp.words[w]) & tp.mask[w];
+        const uint32_t elen = T.b[p + 1], vl = T.b[p + 5 + klen], ll = T.b[p + 7 + klen];
+        // single-byte lengths that nest exactly: entry = key part (klen+2) + 2 + value; value = 2 + list
+        if (diff == 0 && elen < 0x80 && elen == klen + 4 + vl && vl == ll + 2 && p + 2 + elen <= end) {
+          f = (int)next_f; eend = p + 2 + elen; vlen = vl; located = true;
+          p += klen + 6;                                      // at the kind tag
+        }
+      }
+      if (!located) {
+        // ---- generic: 0A elen 0A klen key 12 vlen, key looked up by hash ----
+        uint32_t elen, klen;
+        if (T.b[p] != 0x0A) { bad = true; break; }
+        ++p;
+        if (!t_len(T, p, end, elen) || end - p < elen) { bad = true; break; }
+        eend = p + elen;
+        if (p >= eend || T.b[p] != 0x0A) { bad = true; break; }
+        ++p;
+        if (!t_len(T, p, eend, klen) || eend - p < klen) { bad = true; break; }
+        const uint32_t key = p;
+        p += klen;
+        if (p >= eend || T.b[p] != 0x12) { bad = true; break; }
+        ++p;
+        if (!t_len(T, p, eend, vlen) || p + vlen != eend) { bad = true; break; }
+        uint32_t hi = 0;
+        for (uint32_t i = 0; i < klen; ++i) hi |= T.b[key + i];
+        if (hi >= 0x80 && !utf8_valid(T.b + key, klen)) { bad = true; break; }   // malformed key: the general path reports it
         uint32_t h = name_hash(T.b + key, klen);
         uint32_t slot = h & (uint32_t)A.sch.ht_mask;
         for (;;) {
@@ -251,9 +293,9 @@ __global__ void __launch_bounds__(64) decode_tile_kernel(TileArgs A) {
       if (f >= 0 && sfields[f].elem_type == TFR_T_NULL) f = -1;                 // NullType: always null, value only validated
       if (f >= 0) {
         unsigned long long bit = 1ull << (f & 63);
-        if (f < 64) { if (seen_lo & bit) { bad = true; break; } seen_lo |= bit; }    // duplicate key: last-wins -> general path
+        if (f < 64) { if (seen_lo & bit) { bad = true; break; } seen_lo |= bit; }    // duplicate key (inside this warp's entries)
         else { if (seen_hi & bit) { bad = true; break; } seen_hi |= bit; }
-        next_f = (uint32_t)f + 1;
+        next_f = (uint32_t)f + TILE_PARSE_WARPS;
       }
       // ---- Feature: exactly one oneof member spanning the value ----
       if (vlen == 0) { if (f >= 0) bad = true; p = eend; continue; }              // kind not set: an error if the schema wants it
@@ -389,34 +431,48 @@ __global__ void __launch_bounds__(64) decode_tile_kernel(TileArgs A) {
       p = eend;
     }
   }
-  // ---- validity bitmaps by ballot (rows are 32-aligned), absent fields -> null / error ----
-  const uint32_t act_mask = __ballot_sync(FULLMASK, active);
-  for (uint32_t f0 = 0; f0 < nf; f0 += 32) {
-    uint32_t my_word = 0;
-    const uint32_t lim = min(32u, nf - f0);
-    for (uint32_t j = 0; j < lim; ++j) {
-      const uint32_t f = f0 + j;
-      const bool present = f < 64 ? (seen_lo >> f) & 1 : (seen_hi >> (f - 64)) & 1;
-      const uint32_t m = __ballot_sync(FULLMASK, present && active);
-      if (lane == j) my_word = m;
-      if (active && !present && sfields[f].elem_type != TFR_T_NULL) {
-        const DevField& fd = sfields[f];
-        if (!fd.nullable) bad = true;                                         // NullPointerException: error path
-        if (fd.fix_slot >= 0) {
-          void* vp = A.fix_values[fd.fix_slot];
-          if (fd.width == 8) reinterpret_cast<uint64_t*>(vp)[row] = 0; else reinterpret_cast<uint32_t*>(vp)[row] = 0;
-        } else if (fd.var_slot >= 0) {
-          const int32_t ul = A.uniform_len[fd.var_slot];
-          if (ul > 0) shape_bad = 1;                                          // a null row has no values: not uniform
-          else if (ul < 0) for (int l = 0; l < fd.n_levels; ++l) A.cnt[(size_t)(fd.cnt_slot + l) * A.n + row] = 0;
+  // ---- merge the parse warps' seen masks (a key seen by two warps is a duplicate) ----
+  sseen[(wid * 32 + lane) * 2] = seen_lo;
+  sseen[(wid * 32 + lane) * 2 + 1] = seen_hi;
+  asm volatile("bar.sync 1, %0;" ::"r"(TILE_PARSE_WARPS * 32) : "memory");
+  if (wid == 0) {
+    unsigned long long all_lo = 0, all_hi = 0;
+#pragma unroll
+    for (int w = 0; w < TILE_PARSE_WARPS; ++w) {
+      unsigned long long a = sseen[(w * 32 + lane) * 2], b = sseen[(w * 32 + lane) * 2 + 1];
+      if ((all_lo & a) | (all_hi & b)) bad = true;                            // duplicate key across warps: last-wins -> general path
+      all_lo |= a; all_hi |= b;
+    }
+    seen_lo = all_lo; seen_hi = all_hi;
+    // ---- validity bitmaps by ballot (rows are 32-aligned), absent fields -> null / error ----
+    const uint32_t act_mask = __ballot_sync(FULLMASK, active);
+    for (uint32_t f0 = 0; f0 < nf; f0 += 32) {
+      uint32_t my_word = 0;
+      const uint32_t lim = min(32u, nf - f0);
+      for (uint32_t j = 0; j < lim; ++j) {
+        const uint32_t f = f0 + j;
+        const bool present = f < 64 ? (seen_lo >> f) & 1 : (seen_hi >> (f - 64)) & 1;
+        const uint32_t m = __ballot_sync(FULLMASK, present && active);
+        if (lane == j) my_word = m;
+        if (active && !present && sfields[f].elem_type != TFR_T_NULL) {
+          const DevField& fd = sfields[f];
+          if (!fd.nullable) bad = true;                                       // NullPointerException: error path
+          if (fd.fix_slot >= 0) {
+            void* vp = A.fix_values[fd.fix_slot];
+            if (fd.width == 8) reinterpret_cast<uint64_t*>(vp)[row] = 0; else reinterpret_cast<uint32_t*>(vp)[row] = 0;
+          } else if (fd.var_slot >= 0) {
+            const int32_t ul = A.uniform_len[fd.var_slot];
+            if (ul > 0) shape_bad = 1;                                        // a null row has no values: not uniform
+            else if (ul < 0) for (int l = 0; l < fd.n_levels; ++l) A.cnt[(size_t)(fd.cnt_slot + l) * A.n + row] = 0;
+          }
         }
       }
-    }
-    if (lane < lim) {
-      const uint32_t f = f0 + lane;
-      reinterpret_cast<uint32_t*>(A.bitmaps + (size_t)f * A.nb_stride)[blockIdx.x] = my_word;
-      const uint32_t nulls = __popc(act_mask & ~my_word);
-      if (nulls) atomicAdd(&A.null_counts[f], (unsigned long long)nulls);
+      if (lane < lim) {
+        const uint32_t f = f0 + lane;
+        reinterpret_cast<uint32_t*>(A.bitmaps + (size_t)f * A.nb_stride)[blockIdx.x] = my_word;
+        const uint32_t nulls = __popc(act_mask & ~my_word);
+        if (nulls) atomicAdd(&A.null_counts[f], (unsigned long long)nulls);
+      }
     }
   }
   if (bad) atomicOr(A.flags, TF_FALLBACK);
