@@ -15,7 +15,7 @@ from ._cabi import HostColumn, column_from_ctypes, make_fields, tfr_batch_info, 
 from .sqltypes import StructType
 
 _DIR = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_DIR, "libtfrgpu.so")
+LIB_PATH = os.environ.get("TFR_LIB") or os.path.join(_DIR, "libtfrgpu.so")   # TFR_LIB: tuning builds only
 _LIB = None
 
 # every symbol include/tfrgpu.h declares

@@ -105,6 +105,7 @@ static void build_crc_tables(CrcTables& t) {
     t.s8[0][i] = t.t0[i];
     for (int k = 1; k < 8; ++k) t.s8[k][i] = (t.s8[k - 1][i] >> 8) ^ t.t0[t.s8[k - 1][i] & 0xff];
   }
+  for (uint32_t m = 0; m < 128; ++m) t.xp512[m] = xpow_bytes(512 * m);
 }
 
 static int32_t get_ctx(int device, DeviceCtx** out) {

@@ -25,6 +25,7 @@ struct CrcTables {
   uint32_t k128[4][256];
   uint32_t xw[40];
   uint32_t s8[8][256];   // slicing-by-8 tables (tile.cuh: one record per thread, serial CRC from shared memory)
+  uint32_t xp512[128];   // x^(8*512*m) mod P: shifts a 512-byte segment's CRC state over m later segments
 };
 #define CRC_SMEM_WORDS (256 + 1024 + 40)
 

@@ -34,7 +34,9 @@
 #include "decode.cuh"
 
 #define TILE_ROWS 32
-#define TILE_PARSE_WARPS 4
+#ifndef TILE_PARSE_WARPS
+#define TILE_PARSE_WARPS 6
+#endif
 #define TILE_THREADS ((TILE_PARSE_WARPS + 1) * 32)
 #define TILE_TPL_WORDS 5          // template covers up to 20 bytes: key names up to 12 bytes
 
@@ -125,40 +127,75 @@ __device__ __forceinline__ bool t_len(const Tile& t, uint32_t& p, uint32_t end, 
   return false;
 }
 
-// serial slicing-by-8 CRC-32C over shared memory; s8 = 8 tables of 256 words
-__device__ __forceinline__ uint32_t crc_serial_s8(const uint32_t* s8, const uint8_t* base, uint32_t o, uint32_t n) {
-  uint32_t c = 0xFFFFFFFFu;
+// ---- per-thread CRC-32C over shared memory: slicing-by-8 with instruction-level parallelism ----
+// One 8-byte step of the register: s8 = 8 tables of 256 words.
+__device__ __forceinline__ uint32_t crc_fold8(const uint32_t* s8, uint32_t c, uint32_t lo, uint32_t hi) {
+  uint32_t a = lo ^ c;
+  return s8[7 * 256 + (a & 0xff)] ^ s8[6 * 256 + ((a >> 8) & 0xff)] ^ s8[5 * 256 + ((a >> 16) & 0xff)] ^ s8[4 * 256 + (a >> 24)] ^
+         s8[3 * 256 + (hi & 0xff)] ^ s8[2 * 256 + ((hi >> 8) & 0xff)] ^ s8[1 * 256 + ((hi >> 16) & 0xff)] ^ s8[(hi >> 24)];
+}
+// serial: state `c` over n bytes at tile offset o (any alignment)
+__device__ __forceinline__ uint32_t crc_serial_s8(const uint32_t* s8, const uint8_t* base, uint32_t o, uint32_t n, uint32_t c) {
   while (n && (o & 3)) { c = (c >> 8) ^ s8[(c ^ base[o++]) & 0xff]; --n; }
   const uint32_t* w = reinterpret_cast<const uint32_t*>(base + o);
   uint32_t nw = n >> 3;
 #pragma unroll 2
-  for (uint32_t i = 0; i < nw; ++i) {
-    uint32_t a = w[2 * i] ^ c, b = w[2 * i + 1];
-    c = s8[7 * 256 + (a & 0xff)] ^ s8[6 * 256 + ((a >> 8) & 0xff)] ^ s8[5 * 256 + ((a >> 16) & 0xff)] ^ s8[4 * 256 + (a >> 24)] ^
-        s8[3 * 256 + (b & 0xff)] ^ s8[2 * 256 + ((b >> 8) & 0xff)] ^ s8[1 * 256 + ((b >> 16) & 0xff)] ^ s8[(b >> 24)];
-  }
+  for (uint32_t i = 0; i < nw; ++i) c = crc_fold8(s8, c, w[2 * i], w[2 * i + 1]);
   o += nw * 8; n &= 7;
   while (n--) c = (c >> 8) ^ s8[(c ^ base[o++]) & 0xff];
-  return ~c;
+  return c;
+}
+// A serial CRC is one long dependent chain (one table-lookup round trip per 8 bytes).  The payload is cut
+// into 512-byte segments; three segment chains run interleaved in the same thread (independent
+// registers -> the LDS latencies overlap), each segment state is shifted over the segments that follow
+// it with ONE GF(2) multiply by the table constant x^(8*512*m) (xp512, in shared memory) and the
+// < 512-byte tail is folded serially from the combined state.  CRC(A||B) = CRC_B(0) ^ shift_|B|(CRC_A).
+#define CRC_SEG 512u
+__device__ __forceinline__ uint32_t crc_segmented(const uint32_t* s8, const uint32_t* xp, const uint8_t* base, uint32_t o, uint32_t n) {
+  const uint32_t nF = n / CRC_SEG;
+  if (nF == 0 || nF > 127) return ~crc_serial_s8(s8, base, o, n, 0xFFFFFFFFu);
+  const uint32_t sh = (o & 3u) * 8;
+  const uint32_t* W = reinterpret_cast<const uint32_t*>(base + (o & ~3u));     // aligned words; chain k starts at W + k*128
+  uint32_t acc = 0, j = 0;
+  for (; j + 3 <= nF; j += 3) {
+    const uint32_t* w0 = W + j * (CRC_SEG / 4);
+    const uint32_t* w1 = w0 + CRC_SEG / 4;
+    const uint32_t* w2 = w1 + CRC_SEG / 4;
+    uint32_t c0 = j == 0 ? 0xFFFFFFFFu : 0u, c1 = 0, c2 = 0;
+    uint32_t k0 = w0[0], k1 = w1[0], k2 = w2[0];                               // carry words for the funnel shifts
+#pragma unroll 4
+    for (uint32_t i = 0; i < CRC_SEG / 8; ++i) {
+      uint32_t a0 = w0[2 * i + 1], b0 = w0[2 * i + 2], a1 = w1[2 * i + 1], b1 = w1[2 * i + 2], a2 = w2[2 * i + 1], b2 = w2[2 * i + 2];
+      c0 = crc_fold8(s8, c0, __funnelshift_r(k0, a0, sh), __funnelshift_r(a0, b0, sh)); k0 = b0;
+      c1 = crc_fold8(s8, c1, __funnelshift_r(k1, a1, sh), __funnelshift_r(a1, b1, sh)); k1 = b1;
+      c2 = crc_fold8(s8, c2, __funnelshift_r(k2, a2, sh), __funnelshift_r(a2, b2, sh)); k2 = b2;
+    }
+    acc ^= gf2_mulmod(xp[nF - 1 - j], c0) ^ gf2_mulmod(xp[nF - 2 - j], c1) ^ gf2_mulmod(xp[nF - 3 - j], c2);
+  }
+  for (; j < nF; ++j) {
+    uint32_t c = crc_serial_s8(s8, base, o + j * CRC_SEG, CRC_SEG, j == 0 ? 0xFFFFFFFFu : 0u);
+    acc ^= gf2_mulmod(xp[nF - 1 - j], c);
+  }
+  return ~crc_serial_s8(s8, base, o + nF * CRC_SEG, n - nF * CRC_SEG, acc);
 }
 
 // shared memory layout (dynamic), all sections 16-byte aligned:
-//   [0,16) mbarrier | CRC tables 8 KiB | seen masks [W][32][2] u64 | DevField[nf] | FieldTemplate[nf] | names | tile bytes
+//   [0,16) mbarrier | CRC tables 8 KiB + xp512 512 B | seen masks [W][32][2] u64 | DevField[nf] | FieldTemplate[nf] | names | tile bytes
 #define TILE_SEEN_BYTES (TILE_PARSE_WARPS * 32 * 16)
 __host__ __device__ inline uint32_t tile_schema_smem(uint32_t nf, uint32_t names_bytes) {
   return ((nf * (uint32_t)sizeof(DevField) + 15u) & ~15u) + ((nf * (uint32_t)sizeof(FieldTemplate) + 15u) & ~15u) + ((names_bytes + 15u) & ~15u);
 }
 __host__ __device__ inline uint32_t tile_smem_bytes(uint32_t nf, uint32_t names_bytes, uint32_t tile_cap) {
-  return 16 + 8192 + TILE_SEEN_BYTES + tile_schema_smem(nf, names_bytes) + tile_cap + 64;   // +64: template compares may look a few bytes past the tile
+  return 16 + 8192 + 512 + TILE_SEEN_BYTES + tile_schema_smem(nf, names_bytes) + tile_cap + 64;   // +64: template compares may look a few bytes past the tile
 }
 
 __global__ void __launch_bounds__(TILE_THREADS) decode_tile_kernel(TileArgs A) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
   uint32_t* s8 = reinterpret_cast<uint32_t*>(smem_raw + 16);                               // 8 KiB
-  unsigned long long* sseen = reinterpret_cast<unsigned long long*>(smem_raw + 16 + 8192);
+  unsigned long long* sseen = reinterpret_cast<unsigned long long*>(smem_raw + 16 + 8192 + 512);
   const uint32_t nf = (uint32_t)A.sch.n_fields;
-  uint8_t* sbase = smem_raw + 16 + 8192 + TILE_SEEN_BYTES;
+  uint8_t* sbase = smem_raw + 16 + 8192 + 512 + TILE_SEEN_BYTES;
   DevField* sfields = reinterpret_cast<DevField*>(sbase);
   FieldTemplate* stpl = reinterpret_cast<FieldTemplate*>(sbase + ((nf * (uint32_t)sizeof(DevField) + 15u) & ~15u));
   uint8_t* snames = sbase + ((nf * (uint32_t)sizeof(DevField) + 15u) & ~15u) + ((nf * (uint32_t)sizeof(FieldTemplate) + 15u) & ~15u);
@@ -191,7 +228,7 @@ __global__ void __launch_bounds__(TILE_THREADS) decode_tile_kernel(TileArgs A) {
   }
   {   // meanwhile: CRC tables + schema into shared memory
     const uint32_t* g = reinterpret_cast<const uint32_t*>(A.tabs->s8);
-    for (uint32_t i = threadIdx.x; i < 2048; i += TILE_THREADS) s8[i] = g[i];
+    for (uint32_t i = threadIdx.x; i < 2048 + 128; i += TILE_THREADS) s8[i] = g[i];      // s8 tables, then xp512 (contiguous in CrcTables)
     const uint32_t* gf = reinterpret_cast<const uint32_t*>(A.sch.fields);
     uint32_t* sf = reinterpret_cast<uint32_t*>(sfields);
     for (uint32_t i = threadIdx.x; i < nf * (uint32_t)(sizeof(DevField) / 4); i += TILE_THREADS) sf[i] = gf[i];
@@ -214,7 +251,7 @@ __global__ void __launch_bounds__(TILE_THREADS) decode_tile_kernel(TileArgs A) {
   // =============================== last warp: CRC ===============================
   if (wid == TILE_PARSE_WARPS) {
     if (active && A.verify) {
-      uint32_t crc = crc_serial_s8(s8, tile_b, pay, len);
+      uint32_t crc = crc_segmented(s8, s8 + 2048, tile_b, pay, len);
       if (crc_mask(crc) != t_u32(T, end)) atomicOr(A.flags, TF_FALLBACK);      // the general path reports CRC_DATA at the right record
     }
     return;
