@@ -35,7 +35,7 @@
 
 #define TILE_ROWS 32
 #ifndef TILE_PARSE_WARPS
-#define TILE_PARSE_WARPS 6
+#define TILE_PARSE_WARPS 8     // power of two
 #endif
 #define TILE_THREADS ((TILE_PARSE_WARPS + 1) * 32)
 #define TILE_TPL_WORDS 5          // template covers up to 20 bytes: key names up to 12 bytes
@@ -268,13 +268,16 @@ __global__ void __launch_bounds__(TILE_THREADS) decode_tile_kernel(TileArgs A) {
     if (len < 2 || T.b[p] != 0x0A) bad = true;
     else { ++p; if (!t_len(T, p, end, L) || p + L != end) bad = true; }
     uint32_t next_f = wid;                 // in-order data: this warp's k-th owned entry is field wid + k*W
-    while (!bad && p < end) {
-      if (entry_idx++ % TILE_PARSE_WARPS != wid) {
-        // not ours: hop.  The owner validates the entry; here only stay inside the record.
-        uint32_t b1 = end - p >= 2 ? T.b[p + 1] : 0x80;
-        if (b1 < 0x80) p += 2 + b1;
-        else { ++p; uint32_t el; if (!t_len(T, p, end, el)) { bad = true; break; } p += el; }
-        if (p > end) { bad = true; break; }
+    while (p < end) {
+      if ((entry_idx++ & (TILE_PARSE_WARPS - 1)) != wid) {
+        // not ours: hop over `0A elen ...`.  The owner validates the entry; p + 1 <= end is always inside the
+        // tile (the CRC footer follows the payload) and an overshoot is caught by the p == end check below.
+        const uint32_t b1 = T.b[p + 1];
+        if (b1 < 0x80) { p += 2 + b1; continue; }
+        ++p;
+        uint32_t el;
+        if (!t_len(T, p, end, el)) { bad = true; break; }
+        p += el;
         continue;
       }
       // ---- owned entry: try the expected field's template first ----
@@ -467,6 +470,7 @@ __global__ void __launch_bounds__(TILE_THREADS) decode_tile_kernel(TileArgs A) {
       }
       p = eend;
     }
+    if (p != end) bad = true;
   }
   // ---- merge the parse warps' seen masks (a key seen by two warps is a duplicate) ----
   sseen[(wid * 32 + lane) * 2] = seen_lo;
