@@ -179,49 +179,79 @@ def workload_config(args, n_records, batch_bytes, extra=None):
 # clocks
 # ---------------------------------------------------------------------------------------------
 class ClockSampler:
-    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    """SM clock + throttle reasons sampled with NVML every ~2 ms DURING the timed regions (resident + e2e);
+    falls back to `nvidia-smi -lms` when pynvml is unavailable."""
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
     def __init__(self, index):
         self.index = index
-        self.proc = None
-        self.lines = []
+        self.sm, self.reasons, self.max = [], set(), None
+        self._stop = threading.Event()
+        self.th = None
+        self.mode = None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.th = threading.Thread(target=self._read, daemon=True)
+            import pynvml
+            pynvml.nvmlInit()
+            # CUDA_VISIBLE_DEVICES may remap indices; the box exposes GPUs in order
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = int(vis.split(",")[self.index]) if vis and vis.split(",")[self.index].isdigit() else self.index
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            self.max = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.nv = pynvml
+            self.mode = "nvml"
+            self.th = threading.Thread(target=self._poll, daemon=True)
             self.th.start()
         except Exception:
-            self.proc = None
+            self.mode = "smi"
+            try:
+                q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+                self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "50"],
+                                             stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                self.lines = []
+                self.th = threading.Thread(target=lambda: [self.lines.append(l.strip()) for l in self.proc.stdout], daemon=True)
+                self.th.start()
+            except Exception:
+                self.mode = None
 
-    def _read(self):
-        for ln in self.proc.stdout:
-            self.lines.append(ln.strip())
+    def _poll(self):
+        nv = self.nv
+        while not self._stop.is_set():
+            try:
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h) if hasattr(nv, "nvmlDeviceGetCurrentClocksEventReasons") else nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in self.REASONS.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.002)
 
     def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
-        sm, mx, reasons = [], None, set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
-            p = [x.strip() for x in ln.split(",")]
-            if len(p) < 6:
-                continue
-            try:
-                sm.append(float(p[0])); mx = float(p[1])
-            except ValueError:
-                continue
-            for nm, v in zip(names, p[2:6]):
-                if v.lower().startswith("active"):
-                    reasons.add(nm)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+        if self.mode == "nvml":
+            self._stop.set()
+            self.th.join(timeout=1)
+            return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": self.max, "reasons": sorted(self.reasons),
+                    "samples": len(self.sm), "source": "nvml, 2 ms period, resident + e2e timed regions"}
+        if self.mode == "smi":
+            time.sleep(0.1)
+            self.proc.terminate()
+            sm, mx, reasons = [], None, set()
+            names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+            for ln in self.lines:
+                p = [x.strip() for x in ln.split(",")]
+                if len(p) < 6:
+                    continue
+                try:
+                    sm.append(float(p[0])); mx = float(p[1])
+                except ValueError:
+                    continue
+                for nm, v in zip(names, p[2:6]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nm)
+            return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm), "source": "nvidia-smi -lms 50"}
+        return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["clock sampling unavailable"], "samples": 0}
 
 
 # ---------------------------------------------------------------------------------------------
@@ -276,7 +306,6 @@ def run_ours(args):
     ev1.record(stream)
     barrier()
     t_wall = time.perf_counter() - t_wall0
-    clk = clocks.stop()
     ms = ev0.elapsed_time(ev1)
     prof = dec.get_profile()
     dec.set_profiling(False)
@@ -323,6 +352,8 @@ def run_ours(args):
         e2e = (e2e_bytes, t_e2e, d2h[0])
         for d in decs:
             d.close()
+
+    clk = clocks.stop()
 
     # ---------------- reduce over ranks ----------------
     if use_dist:

@@ -361,8 +361,8 @@ extern "C" int32_t tfr_decoder_create(const tfr_schema* schema, int32_t device, 
   TRY(d->small.ensure(4096 + (size_t)d->schema.n_cnt * 16));
   {
     // fast path eligibility (tile.cuh): Example records, scalars and 1-D arrays, at most 128 fields
-    bool ok = d->schema.record_type == TFR_RT_EXAMPLE && d->schema.fields.size() <= 128 && !getenv("TFR_DISABLE_FAST");
-    for (const DevField& f : d->schema.fields) if (f.depth > 1) ok = false;
+    bool ok = d->schema.record_type != TFR_RT_BYTE_ARRAY && d->schema.fields.size() <= 128 && !getenv("TFR_DISABLE_FAST");
+    for (const DevField& f : d->schema.fields) if (f.depth > 1 && d->schema.record_type == TFR_RT_EXAMPLE) ok = false;
     d->fast_ok = ok;
     if (getenv("TFR_DISABLE_SPECULATION")) d->spec_state = -1;
     d->spec_len.assign(std::max(1, d->schema.n_var), -1);
@@ -600,7 +600,9 @@ static int32_t finish_var_and_views(DecodeCtx& C, DecodeArgs& A, uint32_t n_eff,
     A.n_eff = n_eff;
     if (n_eff > 0 && S.n_var > 0) {
       const uint32_t warps = 8;
-      uint32_t g2 = std::min<uint32_t>((n_eff + warps - 1) / warps, (uint32_t)d->ctx->sm_count * 16);
+      unsigned long long cells = S.record_type == TFR_RT_BYTE_ARRAY ? (unsigned long long)n_eff * 32 : (unsigned long long)n_eff * S.n_var;
+      uint32_t g2 = (uint32_t)std::min<unsigned long long>((cells + 255) / 256, (unsigned long long)d->ctx->sm_count * 16);
+      g2 = std::max<uint32_t>(g2, 1);
       d->span_begin(3);
       decode_pass2_kernel<<<g2, warps * 32, 0, st>>>(A);
       d->span_end(1);
@@ -641,8 +643,14 @@ static int32_t finish_var_and_views(DecodeCtx& C, DecodeArgs& A, uint32_t n_eff,
   return TFR_OK;
 }
 
+static int32_t decode_impl(tfr_decoder* d, const void* data, size_t nbytes, int32_t data_on_device, int32_t is_final, tfr_batch** out,
+                           size_t* consumed, bool allow_fast);
 extern "C" int32_t tfr_decode(tfr_decoder* d, const void* data, size_t nbytes, int32_t data_on_device, int32_t is_final, tfr_batch** out,
                               size_t* consumed) {
+  return decode_impl(d, data, nbytes, data_on_device, is_final, out, consumed, true);
+}
+static int32_t decode_impl(tfr_decoder* d, const void* data, size_t nbytes, int32_t data_on_device, int32_t is_final, tfr_batch** out,
+                           size_t* consumed, bool allow_fast) {
   if (!d || !out || (nbytes && !data)) return fail(TFR_E_INVALID_ARG, "null argument");
   if (nbytes >= (1ull << 31)) return fail(TFR_E_BATCH_TOO_LARGE, "tfr_decode: a batch must be smaller than 2 GiB; split the file at record boundaries");
   CUDA_TRY(cudaSetDevice(d->device));
@@ -668,9 +676,12 @@ extern "C" int32_t tfr_decode(tfr_decoder* d, const void* data, size_t nbytes, i
     C.d_data = (const uint8_t*)d->in.p;
   }
   // ---- K1: record boundaries ----
+  // On the fast path the chain trusts the length fields (pure pointer chase) and the tile kernel's CRC warp
+  // verifies every length CRC from shared memory; if anything is off, K1 is redone with verification.
   FrameResult fr{};
   fr.stop = FS_EOF;
-  if (nbytes) {
+  bool k1_verified = true;
+  auto run_k1 = [&](bool verify_headers) -> int32_t {
     C.chunk_bytes = pick_chunk_bytes(nbytes, d->ctx->sm_count);
     C.n_chunks = (uint32_t)((nbytes + C.chunk_bytes - 1) / C.chunk_bytes);
     TRY(d->chunks.ensure((size_t)C.n_chunks * sizeof(ChunkInfo)));
@@ -680,10 +691,11 @@ extern "C" int32_t tfr_decode(tfr_decoder* d, const void* data, size_t nbytes, i
     d->h_stats->frame = init;
     CUDA_TRY(cudaMemcpyAsync(d_fr, &d->h_stats->frame, sizeof(FrameResult), cudaMemcpyHostToDevice, st));
     uint32_t grid = std::min<uint32_t>((C.n_chunks + 7) / 8, (uint32_t)d->ctx->sm_count * 8);
+    const uint32_t v = verify_headers ? C.verify : 0u;
     d->span_begin(0);
-    frame_scan_kernel<<<grid, 256, 0, st>>>(C.d_data, (uint32_t)nbytes, C.chunk_bytes, C.n_chunks, C.verify, d->ctx->d_tabs, (ChunkInfo*)d->chunks.p, d_fr);
+    frame_scan_kernel<<<grid, 256, 0, st>>>(C.d_data, (uint32_t)nbytes, C.chunk_bytes, C.n_chunks, v, d->ctx->d_tabs, (ChunkInfo*)d->chunks.p, d_fr);
     frame_check_kernel<<<(C.n_chunks + 255) / 256, 256, 0, st>>>((const ChunkInfo*)d->chunks.p, C.n_chunks, d_fr);
-    frame_repair_kernel<<<1, 32, 0, st>>>(C.d_data, (uint32_t)nbytes, C.chunk_bytes, C.n_chunks, C.verify, d->ctx->d_tabs, (ChunkInfo*)d->chunks.p, d_fr);
+    frame_repair_kernel<<<1, 32, 0, st>>>(C.d_data, (uint32_t)nbytes, C.chunk_bytes, C.n_chunks, v, d->ctx->d_tabs, (ChunkInfo*)d->chunks.p, d_fr);
     frame_finish_kernel<<<1, 1024, 0, st>>>((const ChunkInfo*)d->chunks.p, C.n_chunks, (uint32_t)nbytes, (uint32_t*)d->chunk_base.p, d_fr);
     d->span_end(4);
     CUDA_TRY(cudaMemcpyAsync(&d->h_stats->frame, d_fr, sizeof(FrameResult), cudaMemcpyDeviceToHost, st));
@@ -691,7 +703,13 @@ extern "C" int32_t tfr_decode(tfr_decoder* d, const void* data, size_t nbytes, i
     CUDA_TRY(cudaGetLastError());
     fr = d->h_stats->frame;
     C.n = fr.n_records;
-  }
+    C.rec_off_ready = false;
+    k1_verified = verify_headers || !C.verify;
+    return TFR_OK;
+  };
+  const bool try_fast = allow_fast && d->fast_ok;
+  if (nbytes) TRY(run_k1(!try_fast));
+  if (nbytes && !k1_verified && frame_stop_to_error(fr.stop, is_final != 0) != TFR_OK) TRY(run_k1(true));   // a framing problem: get the exact verdict
   const uint32_t n = C.n;
   int32_t frame_err = frame_stop_to_error(fr.stop, is_final != 0);
   size_t used = nbytes;
@@ -716,7 +734,7 @@ extern "C" int32_t tfr_decode(tfr_decoder* d, const void* data, size_t nbytes, i
     const uint32_t names_bytes = (uint32_t)S.names.size();
     const uint32_t tile_cap = (uint32_t)align_up((size_t)TILE_ROWS * ((size_t)fr.max_len + 16) + 32, 128);
     const size_t tile_smem = tile_smem_bytes(nf, names_bytes, tile_cap);
-    if (d->fast_ok && tile_smem <= (size_t)d->ctx->max_smem_optin) {
+    if (try_fast && tile_smem <= (size_t)d->ctx->max_smem_optin) {
       const bool uniform = d->spec_state == 1;
       TRY(ensure_rec_off(C));
       fill_decode_args(C, A);
@@ -800,6 +818,13 @@ extern "C" int32_t tfr_decode(tfr_decoder* d, const void* data, size_t nbytes, i
       if (done) { n_eff = n; sum.n_eff = n; }
     }
     // ================= general path: warp per record, full protobuf semantics =================
+    if (!done && !k1_verified) {
+      // the fast path could not vouch for this batch and the length CRCs were never checked: start over with the
+      // exact path (frame index with verification + general kernels); the input is already on the device
+      const uint8_t* dev_in = C.d_data;
+      guard.reset();
+      return decode_impl(d, dev_in, nbytes, 1, is_final, out, consumed, false);
+    }
     if (!done) {
       // (a failed fast attempt may have touched the null counters)
       CUDA_TRY(cudaMemsetAsync(b->d_null_counts, 0, sizeof(unsigned long long) * std::max<uint32_t>(nf, 1), st));

@@ -558,16 +558,24 @@ __device__ __forceinline__ void step_feature_emit(Cur body, ElemSink& s) {
 __global__ void __launch_bounds__(256) decode_pass2_kernel(DecodeArgs A) {
   const uint32_t warps = blockDim.x >> 5, wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t nvar = (uint32_t)A.sch.n_var;
-  for (uint32_t row = blockIdx.x * warps + wid; row < A.n_eff; row += gridDim.x * warps) {
-    if (A.sch.record_type == TFR_RT_BYTE_ARRAY) {
+  if (A.sch.record_type == TFR_RT_BYTE_ARRAY) {
+    for (uint32_t row = blockIdx.x * warps + wid; row < A.n_eff; row += gridDim.x * warps) {
       // whole-warp copy of the payload
       const uint8_t* s = A.data + A.src[row];
       uint8_t* d = reinterpret_cast<uint8_t*>(A.var_values[0]) + A.scan[0][row];
       uint32_t l = (uint32_t)(A.scan[0][row + 1] - A.scan[0][row]);
       for (uint32_t i = lane; i < l; i += 32) d[i] = s[i];
-      continue;
     }
-    for (uint32_t v = lane; v < nvar; v += 32) {
+    return;
+  }
+  // one thread per (row, variable-width cell), cells of a row adjacent: every lane has work whatever the
+  // number of variable-width columns is
+  const unsigned long long total = (unsigned long long)A.n_eff * nvar;
+  for (unsigned long long cidx = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; cidx < total; cidx += (unsigned long long)gridDim.x * blockDim.x) {
+    const uint32_t row = (uint32_t)(cidx / nvar);
+    {
+      const uint32_t v = (uint32_t)(cidx % nvar);
+      {
       const int f = A.var_field[v];
       const DevField& fd = A.sch.fields[f];
       const int32_t off0 = A.scan[fd.cnt_slot][row];
@@ -645,6 +653,7 @@ __global__ void __launch_bounds__(256) decode_pass2_kernel(DecodeArgs A) {
         Cur e{A.data + src, A.data + src + 16};
         uint64_t elen; if (!rd_varint64(e, elen)) continue;
         entry_feature_emit(Cur{e.p, e.p + (uint32_t)elen}, s);
+      }
       }
     }
   }

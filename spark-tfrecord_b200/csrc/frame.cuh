@@ -91,8 +91,12 @@ __global__ void __launch_bounds__(256) frame_scan_kernel(const uint8_t* __restri
         uint32_t p = p0 + lane;
         bool hit = false;
         if (p < ce && nbytes - p >= 12) {
-          uint32_t lo = load_u32_unaligned(data + p), hi = load_u32_unaligned(data + p + 4);
-          if (hi == 0 && lo <= 0x7fffffffu) hit = crc_mask(crc_u64(t0, lo, hi)) == load_u32_unaligned(data + p + 8);
+          // cheapest test first: the upper half of a plausible length is zero (one load instead of three)
+          uint32_t hi = load_u32_unaligned(data + p + 4);
+          if (hi == 0) {
+            uint32_t lo = load_u32_unaligned(data + p);
+            if (lo <= 0x7fffffffu) hit = crc_mask(crc_u64(t0, lo, hi)) == load_u32_unaligned(data + p + 8);
+          }
         }
         uint32_t m = __ballot_sync(FULLMASK, hit);
         if (m) first = p0 + (uint32_t)(__ffs(m) - 1);

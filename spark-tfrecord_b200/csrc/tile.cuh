@@ -251,8 +251,10 @@ __global__ void __launch_bounds__(TILE_THREADS) decode_tile_kernel(TileArgs A) {
   // =============================== last warp: CRC ===============================
   if (wid == TILE_PARSE_WARPS) {
     if (active && A.verify) {
+      // the frame index chained the headers without checking them on the fast path: check the length CRC here
+      if (crc_mask(crc_u64(s8, t_u32(T, pay - 12), t_u32(T, pay - 8))) != t_u32(T, pay - 4)) atomicOr(A.flags, TF_FALLBACK);
       uint32_t crc = crc_segmented(s8, s8 + 2048, tile_b, pay, len);
-      if (crc_mask(crc) != t_u32(T, end)) atomicOr(A.flags, TF_FALLBACK);      // the general path reports CRC_DATA at the right record
+      if (crc_mask(crc) != t_u32(T, end)) atomicOr(A.flags, TF_FALLBACK);      // the general path reports the error at the right record
     }
     return;
   }
@@ -264,11 +266,22 @@ __global__ void __launch_bounds__(TILE_THREADS) decode_tile_kernel(TileArgs A) {
   unsigned long long seen_lo = 0, seen_hi = 0;
   if (active) {
     uint32_t p = pay, L = 0;
-    // Example { features = 1 }: exactly one field spanning the payload
+    uint32_t cend = end, fl_start = end, fl_end = end;      // context/features region = [p, cend), feature_lists = [fl_start, fl_end)
+    // Example { features = 1 } / SequenceExample { context = 1, feature_lists = 2 }: exactly these fields, in this order
     if (len < 2 || T.b[p] != 0x0A) bad = true;
-    else { ++p; if (!t_len(T, p, end, L) || p + L != end) bad = true; }
+    else {
+      ++p;
+      if (!t_len(T, p, end, L) || end - p < L) bad = true;
+      else if (A.sch.record_type == TFR_RT_EXAMPLE) { if (p + L != end) bad = true; }
+      else {
+        cend = p + L;
+        uint32_t q = cend, L2 = 0;
+        if (q >= end || T.b[q] != 0x12) bad = true;
+        else { ++q; if (!t_len(T, q, end, L2) || q + L2 != end) bad = true; else { fl_start = q; fl_end = end; } }
+      }
+    }
     uint32_t next_f = wid;                 // in-order data: this warp's k-th owned entry is field wid + k*W
-    while (p < end) {
+    while (!bad && p < cend) {
       if ((entry_idx++ & (TILE_PARSE_WARPS - 1)) != wid) {
         // not ours: hop over `0A elen ...`.  The owner validates the entry; p + 1 <= end is always inside the
         // tile (the CRC footer follows the payload) and an overshoot is caught by the p == end check below.
@@ -276,7 +289,7 @@ __global__ void __launch_bounds__(TILE_THREADS) decode_tile_kernel(TileArgs A) {
         if (b1 < 0x80) { p += 2 + b1; continue; }
         ++p;
         uint32_t el;
-        if (!t_len(T, p, end, el)) { bad = true; break; }
+        if (!t_len(T, p, cend, el)) { bad = true; break; }
         p += el;
         continue;
       }
@@ -293,7 +306,7 @@ __global__ void __launch_bounds__(TILE_THREADS) decode_tile_kernel(TileArgs A) {
           if ((uint32_t)w < tp.n_words) diff |= (t_u32(T, p + 4 * w) ^ tp.words[w]) & tp.mask[w];
         const uint32_t elen = T.b[p + 1], vl = T.b[p + 5 + klen], ll = T.b[p + 7 + klen];
         // single-byte lengths that nest exactly: entry = key part (klen+2) + 2 + value; value = 2 + list
-        if (diff == 0 && elen < 0x80 && elen == klen + 4 + vl && vl == ll + 2 && p + 2 + elen <= end) {
+        if (diff == 0 && elen < 0x80 && elen == klen + 4 + vl && vl == ll + 2 && p + 2 + elen <= cend) {
           f = (int)next_f; eend = p + 2 + elen; vlen = vl; located = true;
           p += klen + 6;                                      // at the kind tag
         }
@@ -303,7 +316,7 @@ __global__ void __launch_bounds__(TILE_THREADS) decode_tile_kernel(TileArgs A) {
         uint32_t elen, klen;
         if (T.b[p] != 0x0A) { bad = true; break; }
         ++p;
-        if (!t_len(T, p, end, elen) || end - p < elen) { bad = true; break; }
+        if (!t_len(T, p, cend, elen) || cend - p < elen) { bad = true; break; }
         eend = p + elen;
         if (p >= eend || T.b[p] != 0x0A) { bad = true; break; }
         ++p;
@@ -470,7 +483,119 @@ __global__ void __launch_bounds__(TILE_THREADS) decode_tile_kernel(TileArgs A) {
       }
       p = eend;
     }
-    if (p != end) bad = true;
+    if (p != cend) bad = true;
+    // ---- SequenceExample.feature_lists: { 0A elen 0A klen key 12 vlen FeatureList }*, FeatureList = { 0A flen Feature }* ----
+    p = fl_start;
+    while (!bad && p < fl_end) {
+      if ((entry_idx++ & (TILE_PARSE_WARPS - 1)) != wid) {
+        const uint32_t b1 = T.b[p + 1];
+        if (b1 < 0x80) { p += 2 + b1; continue; }
+        ++p;
+        uint32_t el;
+        if (!t_len(T, p, fl_end, el)) { bad = true; break; }
+        p += el;
+        continue;
+      }
+      uint32_t elen, klen, vlen;
+      if (T.b[p] != 0x0A) { bad = true; break; }
+      ++p;
+      const uint32_t entry_pos = p;                           // the entry's length varint: what pass 2's FeatureList walker starts from
+      if (!t_len(T, p, fl_end, elen) || fl_end - p < elen) { bad = true; break; }
+      const uint32_t eend = p + elen;
+      if (p >= eend || T.b[p] != 0x0A) { bad = true; break; }
+      ++p;
+      if (!t_len(T, p, eend, klen) || eend - p < klen) { bad = true; break; }
+      const uint32_t key = p;
+      p += klen;
+      if (p >= eend || T.b[p] != 0x12) { bad = true; break; }
+      ++p;
+      if (!t_len(T, p, eend, vlen) || p + vlen != eend) { bad = true; break; }
+      uint32_t hi = 0;
+      for (uint32_t i = 0; i < klen; ++i) hi |= T.b[key + i];
+      if (hi >= 0x80 && !utf8_valid(T.b + key, klen)) { bad = true; break; }
+      int f = -1;
+      {
+        uint32_t h = name_hash(T.b + key, klen);
+        uint32_t slot = h & (uint32_t)A.sch.ht_mask;
+        for (;;) {
+          int cand = A.sch.ht[slot];
+          if (cand < 0) break;
+          if (sfields[cand].hash == h && sfields[cand].name_len == klen) {
+            const uint8_t* nm = snames + sfields[cand].name_off;
+            uint32_t diff = 0;
+            for (uint32_t i = 0; i < klen; ++i) diff |= T.b[key + i] ^ nm[i];
+            if (diff == 0) { f = cand; break; }
+          }
+          slot = (slot + 1) & (uint32_t)A.sch.ht_mask;
+        }
+      }
+      if (f >= 0 && sfields[f].elem_type == TFR_T_NULL) f = -1;
+      const DevField* fd = f >= 0 ? &sfields[f] : nullptr;
+      if (fd) {
+        if (fd->depth != 2) { bad = true; break; }            // array of heads / scalar from a FeatureList: general path
+        unsigned long long bit = 1ull << (f & 63);
+        // a name present in context AND feature_lists (context wins) or twice here: general path
+        if (f < 64) { if (seen_lo & bit) { bad = true; break; } seen_lo |= bit; }
+        else { if (seen_hi & bit) { bad = true; break; } seen_hi |= bit; }
+      }
+      uint32_t steps = 0, tot_n = 0, tot_bytes = 0;
+      while (p < eend) {                                      // steps
+        uint32_t flen;
+        if (T.b[p] != 0x0A) { bad = true; break; }
+        ++p;
+        if (!t_len(T, p, eend, flen) || eend - p < flen) { bad = true; break; }
+        const uint32_t fend = p + flen;
+        ++steps;
+        if (flen == 0) { if (fd) bad = true; continue; }     // kind not set: an error if the schema wants the column
+        uint32_t kt = T.b[p++], llen;
+        uint32_t kind = kt == 0x0A ? K_BYTES : kt == 0x12 ? K_FLOAT : kt == 0x1A ? K_INT64 : K_NONE;
+        if (kind == K_NONE || !t_len(T, p, fend, llen) || p + llen != fend) { bad = true; break; }
+        if (fd && (uint32_t)fd->kind != kind) { bad = true; break; }
+        if (kind == K_BYTES) {
+          const bool is_str = fd && fd->elem_type == TFR_T_STRING;
+          while (p < fend) {
+            uint32_t bl;
+            if (T.b[p] != 0x0A) { bad = true; break; }
+            ++p;
+            if (!t_len(T, p, fend, bl) || fend - p < bl) { bad = true; break; }
+            if (is_str) {
+              uint32_t acc = 0;
+              for (uint32_t i = 0; i < bl; ++i) acc |= T.b[p + i];
+              if (acc >= 0x80 && !utf8_valid(T.b + p, bl)) { bad = true; break; }
+            }
+            ++tot_n; tot_bytes += bl;
+            p += bl;
+          }
+          if (bad) break;
+        } else if (llen != 0) {
+          uint32_t plen;
+          if (T.b[p] != 0x0A) { bad = true; break; }
+          ++p;
+          if (!t_len(T, p, fend, plen) || p + plen != fend) { bad = true; break; }
+          if (kind == K_FLOAT) {
+            if (plen & 3) { bad = true; break; }
+            tot_n += plen >> 2;
+          } else {
+            uint32_t run = 0;
+            for (uint32_t i = 0; i < plen; ++i) {
+              if (T.b[p + i] & 0x80) { if (++run >= 10) { bad = true; break; } } else { ++tot_n; run = 0; }
+            }
+            if (bad || run) { bad = true; break; }
+          }
+        }
+        p = fend;
+      }
+      if (bad) break;
+      if (fd) {
+        A.cnt[(size_t)fd->cnt_slot * A.n + row] = steps;
+        A.cnt[(size_t)(fd->cnt_slot + 1) * A.n + row] = tot_n;
+        if (fd->n_levels == 3) A.cnt[(size_t)(fd->cnt_slot + 2) * A.n + row] = tot_bytes;
+        A.src[(size_t)fd->var_slot * A.n + row] = entry_pos + g0;
+        A.cflag[(size_t)fd->var_slot * A.n + row] = CF_FLIST;
+      }
+      p = eend;
+    }
+    if (!bad && p != fl_end) bad = true;
   }
   // ---- merge the parse warps' seen masks (a key seen by two warps is a duplicate) ----
   sseen[(wid * 32 + lane) * 2] = seen_lo;
