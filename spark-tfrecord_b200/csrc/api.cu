@@ -768,12 +768,15 @@ static int32_t decode_impl(tfr_decoder* d, const void* data, size_t nbytes, int3
       TA.bitmaps = C.fx + C.bitmaps_off; TA.nb_stride = C.nb_stride; TA.null_counts = b->d_null_counts;
       TA.fix_values = A.fix_values; TA.cnt = A.cnt; TA.src = A.src; TA.cflag = A.cflag;
       TA.uniform_len = (const int32_t*)d->uniform_dev.p; TA.var_values = (void* const*)C.dt_vals; TA.flags = dflags_ptr(d);
+      const bool seq = S.record_type == TFR_RT_SEQUENCE_EXAMPLE;
       if (d->tile_smem_set < tile_smem) {
-        CUDA_TRY(cudaFuncSetAttribute(decode_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_smem));
+        if (seq) CUDA_TRY(cudaFuncSetAttribute(decode_tile_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_smem));
+        else CUDA_TRY(cudaFuncSetAttribute(decode_tile_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_smem));
         d->tile_smem_set = tile_smem;
       }
       d->span_begin(1);
-      decode_tile_kernel<<<(n + TILE_ROWS - 1) / TILE_ROWS, TILE_THREADS, tile_smem, st>>>(TA);
+      if (seq) decode_tile_kernel<true><<<(n + TILE_ROWS - 1) / TILE_ROWS, TILE_THREADS, tile_smem, st>>>(TA);
+      else decode_tile_kernel<false><<<(n + TILE_ROWS - 1) / TILE_ROWS, TILE_THREADS, tile_smem, st>>>(TA);
       d->span_end(1); d->pass1_launches++;
       uint32_t tflags = 0;
       if (uniform) {

@@ -189,6 +189,7 @@ __host__ __device__ inline uint32_t tile_smem_bytes(uint32_t nf, uint32_t names_
   return 16 + 8192 + 512 + TILE_SEEN_BYTES + tile_schema_smem(nf, names_bytes) + tile_cap + 64;   // +64: template compares may look a few bytes past the tile
 }
 
+template <bool SEQ>
 __global__ void __launch_bounds__(TILE_THREADS) decode_tile_kernel(TileArgs A) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
@@ -272,7 +273,7 @@ __global__ void __launch_bounds__(TILE_THREADS) decode_tile_kernel(TileArgs A) {
     else {
       ++p;
       if (!t_len(T, p, end, L) || end - p < L) bad = true;
-      else if (A.sch.record_type == TFR_RT_EXAMPLE) { if (p + L != end) bad = true; }
+      else if (!SEQ) { if (p + L != end) bad = true; }
       else {
         cend = p + L;
         uint32_t q = cend, L2 = 0;
@@ -486,7 +487,7 @@ __global__ void __launch_bounds__(TILE_THREADS) decode_tile_kernel(TileArgs A) {
     if (p != cend) bad = true;
     // ---- SequenceExample.feature_lists: { 0A elen 0A klen key 12 vlen FeatureList }*, FeatureList = { 0A flen Feature }* ----
     p = fl_start;
-    while (!bad && p < fl_end) {
+    while (SEQ && !bad && p < fl_end) {
       if ((entry_idx++ & (TILE_PARSE_WARPS - 1)) != wid) {
         const uint32_t b1 = T.b[p + 1];
         if (b1 < 0x80) { p += 2 + b1; continue; }
