@@ -78,10 +78,26 @@ def make_batches(batch_mib: int, pool: int, seed: int):
 
 
 def host_cores():
+    """host threads this process may really use: the affinity mask capped by the cgroup CPU quota"""
     try:
-        return len(os.sched_getaffinity(0))
+        n = len(os.sched_getaffinity(0))
     except AttributeError:
-        return os.cpu_count() or 1
+        n = os.cpu_count() or 1
+    for path in ("/sys/fs/cgroup/cpu.max", "/sys/fs/cgroup/cpu/cpu.cfs_quota_us"):
+        try:
+            txt = open(path).read().split()
+            if path.endswith("cpu.max"):
+                if txt[0] != "max":
+                    n = min(n, max(1, int(int(txt[0]) / int(txt[1]))))
+            else:
+                q = int(txt[0])
+                per = int(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+                if q > 0:
+                    n = min(n, max(1, q // per))
+            break
+        except Exception:
+            continue
+    return n
 
 
 # ---------------------------------------------------------------------------------------------
@@ -190,6 +206,7 @@ class ClockSampler:
         self._stop = threading.Event()
         self.th = None
         self.mode = None
+        self.period = float(os.environ.get("TFR_CLOCK_PERIOD_S", "0.02"))
 
     def start(self):
         try:
@@ -227,14 +244,14 @@ class ClockSampler:
                         self.reasons.add(name)
             except Exception:
                 pass
-            time.sleep(0.002)
+            time.sleep(self.period)
 
     def stop(self):
         if self.mode == "nvml":
             self._stop.set()
             self.th.join(timeout=1)
             return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": self.max, "reasons": sorted(self.reasons),
-                    "samples": len(self.sm), "source": "nvml, 2 ms period, resident + e2e timed regions"}
+                    "samples": len(self.sm), "source": f"nvml, {int(self.period * 1000)} ms period, resident + e2e timed regions"}
         if self.mode == "smi":
             time.sleep(0.1)
             self.proc.terminate()

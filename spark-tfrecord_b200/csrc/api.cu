@@ -300,6 +300,8 @@ struct tfr_decoder {
   void** h_ptr_tables = nullptr;        // pinned mirror of the device pointer tables
   size_t h_ptr_cap = 0;
   PinnedPool host_pool;
+  DevPool dev_pool;                     // output blocks of the batches
+  std::vector<cudaEvent_t> done_pool;
   // fast path (tile.cuh)
   bool fast_ok = false;
   size_t tile_smem_set = 0;
@@ -389,6 +391,8 @@ static void decoder_unref(tfr_decoder* d) {
   if (d->h_uniform) cudaFreeHost(d->h_uniform);
   if (d->h_ptr_tables) cudaFreeHost(d->h_ptr_tables);
   d->host_pool.release_all();
+  d->dev_pool.release_all();
+  for (cudaEvent_t e : d->done_pool) cudaEventDestroy(e);
   d->spans_resolve();
   for (cudaEvent_t e : d->ev_pool) cudaEventDestroy(e);
   cudaStreamDestroy(d->stream);
@@ -469,7 +473,8 @@ static int32_t alloc_fixed(DecodeCtx& C) {
   C.nullc_off = fixed_bytes; fixed_bytes += align_up(sizeof(unsigned long long) * std::max<uint32_t>(nf, 1), 256);
   for (int i = 0; i < S.n_fix; ++i) { C.fix_off[i] = fixed_bytes; fixed_bytes += align_up((size_t)n * S.fields[S.fix_field[i]].width + 8, 256); }
   for (int v = 0; v < S.n_var; ++v) { C.off0_off[v] = fixed_bytes; fixed_bytes += align_up(((size_t)n + 1) * 4, 256); }
-  CUDA_TRY(cudaMallocAsync(&C.b->dev_fixed, fixed_bytes, C.st));
+  C.b->dev_fixed = C.d->dev_pool.acquire(fixed_bytes);
+  if (!C.b->dev_fixed) return fail(TFR_E_OOM, "device allocation failed (batch outputs)");
   C.b->dev_fixed_bytes = fixed_bytes;
   C.fx = (uint8_t*)C.b->dev_fixed;
   C.b->d_null_counts = (unsigned long long*)(C.fx + C.nullc_off);
@@ -586,7 +591,7 @@ static int32_t finish_var_and_views(DecodeCtx& C, DecodeArgs& A, uint32_t n_eff,
       for (int l = 1; l < fd.n_levels; ++l) { lvl_off[v * 3 + l] = var_bytes; var_bytes += align_up(((size_t)totals[fd.cnt_slot + l - 1] + 1) * 4, 256); }
       val_off[v] = var_bytes; var_bytes += align_up((size_t)totals[fd.cnt_slot + fd.n_levels - 1] * fd.width + 8, 256);
     }
-    if (var_bytes) CUDA_TRY(cudaMallocAsync(&b->dev_var, var_bytes, st));
+    if (var_bytes) { b->dev_var = d->dev_pool.acquire(var_bytes); if (!b->dev_var) return fail(TFR_E_OOM, "device allocation failed (batch outputs)"); }
     b->dev_var_bytes = var_bytes;
     vx = (uint8_t*)b->dev_var;
     for (int v = 0; v < S.n_var; ++v) {
@@ -751,7 +756,7 @@ static int32_t decode_impl(tfr_decoder* d, const void* data, size_t nbytes, int3
           C.t_vals[v] = (void*)var_bytes;                          // offset for now, rebased after the allocation
           var_bytes += align_up((size_t)utot[fd.cnt_slot] * fd.width + 8, 256);
         }
-        if (var_bytes) CUDA_TRY(cudaMallocAsync(&b->dev_var, var_bytes, st));
+        if (var_bytes) { b->dev_var = d->dev_pool.acquire(var_bytes); if (!b->dev_var) return fail(TFR_E_OOM, "device allocation failed (batch outputs)"); }
         b->dev_var_bytes = var_bytes;
         for (int v = 0; v < S.n_var; ++v) {
           C.t_vals[v] = (uint8_t*)b->dev_var + (size_t)C.t_vals[v];
@@ -795,7 +800,7 @@ static int32_t decode_impl(tfr_decoder* d, const void* data, size_t nbytes, int3
           done = true;
         } else {
           if (tflags & TF_SHAPE) d->spec_state = -1;          // shapes are not uniform after all: stop speculating
-          if (b->dev_var) { cudaFreeAsync(b->dev_var, st); b->dev_var = nullptr; b->dev_var_bytes = 0; }
+          if (b->dev_var) { d->dev_pool.give_back(b->dev_var); b->dev_var = nullptr; b->dev_var_bytes = 0; }
         }
       } else {
         TRY(scans_and_sync(C, A, false));
@@ -872,7 +877,8 @@ static int32_t decode_impl(tfr_decoder* d, const void* data, size_t nbytes, int3
   } else if (frame_err) {
     b->info.error_code = frame_err; b->info.error_row = n; b->info.error_field = -1;
   }
-  CUDA_TRY(cudaEventCreateWithFlags(&b->done, cudaEventDisableTiming));
+  if (!d->done_pool.empty()) { b->done = d->done_pool.back(); d->done_pool.pop_back(); }
+  else CUDA_TRY(cudaEventCreateWithFlags(&b->done, cudaEventDisableTiming));
   CUDA_TRY(cudaEventRecord(b->done, st));
   CUDA_TRY(cudaGetLastError());
   guard.release();
@@ -949,10 +955,10 @@ extern "C" void tfr_batch_release(tfr_batch* b) {
   if (b->refs.fetch_sub(1) != 1) return;
   tfr_decoder* d = b->dec;
   cudaSetDevice(d->device);
-  if (b->dev_fixed) cudaFreeAsync(b->dev_fixed, d->stream);
-  if (b->dev_var) cudaFreeAsync(b->dev_var, d->stream);
+  if (b->dev_fixed) d->dev_pool.give_back(b->dev_fixed);
+  if (b->dev_var) d->dev_pool.give_back(b->dev_var);
   if (b->host_copy) d->host_pool.give_back(b->host_copy);
-  if (b->done) cudaEventDestroy(b->done);
+  if (b->done) d->done_pool.push_back(b->done);
   delete b;
   decoder_unref(d);
 }

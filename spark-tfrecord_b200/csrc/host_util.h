@@ -47,6 +47,28 @@ struct PinnedPool {
   void release_all() { for (auto& b : blocks) cudaFreeHost(b.p); blocks.clear(); }
 };
 
+// device blocks reused across batches (all use is ordered on the owning decoder's stream)
+struct DevPool {
+  struct Block { void* p; size_t cap; bool used; };
+  std::vector<Block> blocks;
+  void* acquire(size_t bytes) {
+    int best = -1;
+    for (size_t i = 0; i < blocks.size(); ++i)
+      if (!blocks[i].used && blocks[i].cap >= bytes && (best < 0 || blocks[i].cap < blocks[best].cap)) best = (int)i;
+    if (best >= 0) { blocks[best].used = true; return blocks[best].p; }
+    for (size_t i = 0; i < blocks.size();) {
+      if (!blocks[i].used && blocks.size() > 6) { cudaFree(blocks[i].p); blocks.erase(blocks.begin() + i); } else ++i;
+    }
+    void* p = nullptr;
+    size_t cap = bytes + bytes / 8 + 4096;
+    if (cudaMalloc(&p, cap) != cudaSuccess) { cap = bytes; if (cudaMalloc(&p, cap) != cudaSuccess) return nullptr; }
+    blocks.push_back({p, cap, true});
+    return p;
+  }
+  void give_back(void* p) { for (auto& b : blocks) if (b.p == p) b.used = false; }
+  void release_all() { for (auto& b : blocks) cudaFree(b.p); blocks.clear(); }
+};
+
 extern "C" {
 struct ArrowSchema {
   const char* format; const char* name; const char* metadata; int64_t flags; int64_t n_children;
