@@ -208,7 +208,8 @@ int32_t tfr_encoder_stream(tfr_encoder*, void** cuda_stream);
 /* lattice codes of M/TensorFlowInferSchema.scala:194-207; merge = max, 0 = identity     */
 enum { TFR_INF_NULL = 0, TFR_INF_LONG = 1, TFR_INF_FLOAT = 2, TFR_INF_STRING = 3,
        TFR_INF_ARR_LONG = 4, TFR_INF_ARR_FLOAT = 5, TFR_INF_ARR_STRING = 6,
-       TFR_INF_ARR2_LONG = 7, TFR_INF_ARR2_FLOAT = 8, TFR_INF_ARR2_STRING = 9 };
+       TFR_INF_ARR2_LONG = 7, TFR_INF_ARR2_FLOAT = 8, TFR_INF_ARR2_STRING = 9,
+       TFR_INF_ARR2_NULL = 10 /* ArrayType(ArrayType(null)): a FeatureList whose steps are all empty (:102-107) */ };
 typedef struct tfr_infer tfr_infer;
 int32_t tfr_infer_create(int32_t record_type, int32_t device, tfr_infer** out);
 /* accumulate one block of framed bytes (seqOp of rdd.aggregate, :40,43) */

@@ -792,15 +792,23 @@ static int infer_feature_code(const feature_t* f) {     /* inferField :132-145 +
   int base = f->kind == K_INT64 ? TFR_INF_LONG : f->kind == K_FLOAT ? TFR_INF_FLOAT : TFR_INF_STRING;
   return f->n > 1 ? base + 3 : base;
 }
+static int infer_conflict = 0;
 static void infer_merge(tfr_oracle_infer_t* s, const char* name, uint32_t len, int code) {
   for (size_t i = 0; i < s->n; i++)
-    if (s->e[i].len == len && memcmp(s->e[i].name, name, len) == 0) { if (code > s->e[i].code) s->e[i].code = code; return; }
+    if (s->e[i].len == len && memcmp(s->e[i].name, name, len) == 0) {
+      /* findTightestCommonType: equal -> same; null is the identity; ArrayType(ArrayType(null)) has no precedence -> throws */
+      int old = s->e[i].code;
+      if (old != code && old != TFR_INF_NULL && code != TFR_INF_NULL && (old == TFR_INF_ARR2_NULL || code == TFR_INF_ARR2_NULL)) infer_conflict = 1;
+      if (code > old) s->e[i].code = code;
+      return;
+    }
   if (s->n == s->cap) { s->cap = s->cap ? s->cap * 2 : 16; s->e = (infent_t*)realloc(s->e, s->cap * sizeof(infent_t)); }
   s->e[s->n].name = (char*)malloc(len ? len : 1); memcpy(s->e[s->n].name, name, len);
   s->e[s->n].len = len; s->e[s->n].code = code; s->n++;
 }
 int32_t tfr_oracle_infer(const uint8_t* data, size_t nbytes, int32_t record_type, tfr_oracle_infer_t** out) {
   tfr_oracle_infer_t* s = (tfr_oracle_infer_t*)calloc(1, sizeof *s);
+  infer_conflict = 0;
   record_t rec; memset(&rec, 0, sizeof rec); rec.feature_lists.is_flist = 1;
   size_t pos = 0; int rc = TFR_OK;
   while (nbytes - pos >= 8) {
@@ -815,15 +823,15 @@ int32_t tfr_oracle_infer(const uint8_t* data, size_t nbytes, int32_t record_type
     }
     for (size_t i = 0; i < rec.feature_lists.n && !rc; i++) {   /* inferFeatureListTypes :98-118 */
       featurelist_t* l = &rec.feature_lists.e[i].flist; int c = TFR_INF_NULL;
+      if (l->n == 0) { rc = TFR_E_EMPTY_SCALAR; break; }          /* empty.reduceLeft -> UnsupportedOperationException */
       for (size_t k = 0; k < l->n; k++) {
         int ck = infer_feature_code(&l->f[k]);
         if (ck < 0) { rc = TFR_E_KIND_MISMATCH; break; }
-        if (ck > c) c = ck;
+        if (ck > c) c = ck;                                          /* reduceLeft(findTightestCommonType) */
       }
       if (rc) break;
-      /* element type wrapped in one more ArrayType (:102-107); a scalar step type T becomes
-       * ArrayType(ArrayType(T)) only via the array codes: Long->[[Long]] etc. */
-      if (c != TFR_INF_NULL) { int base = (c - 1) % 3; c = TFR_INF_ARR2_LONG + base; }
+      /* T or ArrayType(T) -> ArrayType(ArrayType(T)) (:102-107); all steps empty -> ArrayType(ArrayType(null)) = 10 */
+      if (c != TFR_INF_NULL) { int base = (c - 1) % 3; c = TFR_INF_ARR2_LONG + base; } else c = TFR_INF_ARR2_NULL;
       infer_merge(s, rec.feature_lists.e[i].key, rec.feature_lists.e[i].key_len, c);
     }
     if (rc) break;
@@ -831,6 +839,7 @@ int32_t tfr_oracle_infer(const uint8_t* data, size_t nbytes, int32_t record_type
   }
   map_clear(&rec.features); map_clear(&rec.feature_lists);
   *out = s;
+  if (!rc && infer_conflict) rc = TFR_E_UNSUPPORTED_TYPE;
   return rc;
 }
 int32_t tfr_oracle_infer_count(tfr_oracle_infer_t* s) { return (int32_t)s->n; }

@@ -335,3 +335,38 @@ class Encoder:
             self.close()
         except Exception:
             pass
+
+
+class Infer:
+    """Schema inference accumulator (tfr_infer_*): update() is the seqOp over one block of framed bytes, result()
+    the merged name -> lattice code map (TFR_INF_*)."""
+
+    def __init__(self, record_type: int = 0, device: int = 0):
+        h = C.c_void_p()
+        _check(lib().tfr_infer_create(record_type, device, C.byref(h)))
+        self.h = h
+
+    def update(self, data):
+        ptr, n, on_dev, keep = _device_ptr(data)
+        _check(lib().tfr_infer_update(self.h, ptr, n, on_dev))
+
+    def result(self) -> dict:
+        n = C.c_int32()
+        _check(lib().tfr_infer_result(self.h, C.byref(n)))
+        out = {}
+        for i in range(n.value):
+            nm = C.c_char_p(); ln = C.c_int32(); code = C.c_int32()
+            _check(lib().tfr_infer_name(self.h, i, C.byref(nm), C.byref(ln), C.byref(code)))
+            out[C.string_at(nm, ln.value)] = code.value
+        return out
+
+    def close(self):
+        if self.h:
+            lib().tfr_infer_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -18,6 +18,7 @@
 #include "encode.cuh"
 #include "frame.cuh"
 #include "host_util.h"
+#include "infer.cuh"
 #include "scan.cuh"
 #include "tile.cuh"
 

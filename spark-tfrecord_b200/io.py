@@ -214,6 +214,30 @@ class DefaultSource:
     def isSplitable(self, *a, **k) -> bool:
         return False                                             # :26-29; splitting happens inside the native side
 
+    def inferSchema(self, options: Dict[str, str], files: Sequence[str], device: int = 0, dist=None):
+        """M/DefaultSource.scala:31-39,48-70: the first non-empty file is scanned (the reference scans it twice);
+        ByteArray has the fixed one-column schema.  With `dist`, every rank scans its shard of the files and the maps
+        are merged with one all-reduce (sharding.allreduce_schema)."""
+        from .sharding import allreduce_schema, codes_to_struct, shard_lpt
+        rt = _record_type(options)
+        if rt == 2:
+            return byte_array_schema()
+        todo = [f for f in files if os.path.getsize(f) > 0]
+        if dist is None or not dist.is_initialized():
+            todo = todo[:1]
+        else:
+            mine = shard_lpt([os.path.getsize(f) for f in todo], dist.get_world_size())[dist.get_rank()]
+            todo = [todo[i] for i in mine]
+        inf = _native.Infer(rt, device)
+        try:
+            for f in todo:
+                with open(f, "rb") as fh:
+                    inf.update(fh.read())
+            local = inf.result()
+        finally:
+            inf.close()
+        return codes_to_struct(allreduce_schema(local, dist, f"cuda:{device}" if dist is not None and dist.is_initialized() and dist.get_backend() == "nccl" else None))
+
     def buildReader(self, dataSchema: StructType, requiredSchema: StructType, options: Dict[str, str], device: int = 0):
         """-> PartitionedFile => Iterator[row] (filters are accepted and ignored, :123)"""
         return lambda file: TFRecordFileReader.readFile(None, options, file, requiredSchema, device)
