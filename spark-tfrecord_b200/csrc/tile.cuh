@@ -283,17 +283,23 @@ __global__ void __launch_bounds__(TILE_THREADS) decode_tile_kernel(TileArgs A) {
     }
     uint32_t next_f = wid;                 // in-order data: this warp's k-th owned entry is field wid + k*W
     while (!bad && p < cend) {
-      if ((entry_idx++ & (TILE_PARSE_WARPS - 1)) != wid) {
-        // not ours: hop over `0A elen ...`.  The owner validates the entry; p + 1 <= end is always inside the
-        // tile (the CRC footer follows the payload) and an overshoot is caught by the p == end check below.
+      // hop over the entries the other parse warps own (`0A elen ...`): a tight loop, one byte load + add per entry.
+      // The owner validates those entries; p + 1 <= cend is always inside the tile and an overshoot is caught by the
+      // p == cend check after the loop.
+      uint32_t skip = (wid - entry_idx) & (TILE_PARSE_WARPS - 1);
+      while (skip && p < cend) {
+        ++entry_idx;
         const uint32_t b1 = T.b[p + 1];
-        if (b1 < 0x80) { p += 2 + b1; continue; }
-        ++p;
-        uint32_t el;
-        if (!t_len(T, p, cend, el)) { bad = true; break; }
-        p += el;
-        continue;
+        if (b1 < 0x80) p += 2 + b1;
+        else {
+          uint32_t q = p + 1, el;
+          if (!t_len(T, q, cend, el)) { bad = true; break; }
+          p = q + el;
+        }
+        --skip;
       }
+      if (bad || p >= cend) break;
+      ++entry_idx;                                           // the entry this warp owns
       // ---- owned entry: try the expected field's template first ----
       uint32_t eend, vlen;
       int f = -1;
@@ -428,12 +434,18 @@ __global__ void __launch_bounds__(TILE_THREADS) decode_tile_kernel(TileArgs A) {
           // varints: count terminators, every run <= 10 bytes, the last byte terminates; first value decoded on the way
           n = 0;
           uint32_t run = 0;
-          for (uint32_t i = 0; i < plen; ++i) {
-            uint32_t b = T.b[pk + i];
-            if (n == 0) v0 |= (uint64_t)(b & 0x7f) << (7 * run);
-            if (b & 0x80) { if (++run >= 10) { bad = true; break; } } else { ++n; run = 0; }
+          if (plen == 1) {                                   // the most common case: one small value
+            v0 = T.b[pk];
+            if (v0 & 0x80) { bad = true; break; }
+            n = 1;
+          } else {
+            for (uint32_t i = 0; i < plen; ++i) {
+              uint32_t b = T.b[pk + i];
+              if (n == 0) v0 |= (uint64_t)(b & 0x7f) << (7 * run);
+              if (b & 0x80) { if (++run >= 10) { bad = true; break; } } else { ++n; run = 0; }
+            }
+            if (bad || run) { bad = true; break; }
           }
-          if (bad || run) { bad = true; break; }
         }
         if (fd) {
           if (fd->depth == 0) {
@@ -488,15 +500,20 @@ __global__ void __launch_bounds__(TILE_THREADS) decode_tile_kernel(TileArgs A) {
     // ---- SequenceExample.feature_lists: { 0A elen 0A klen key 12 vlen FeatureList }*, FeatureList = { 0A flen Feature }* ----
     p = fl_start;
     while (SEQ && !bad && p < fl_end) {
-      if ((entry_idx++ & (TILE_PARSE_WARPS - 1)) != wid) {
+      uint32_t skip = (wid - entry_idx) & (TILE_PARSE_WARPS - 1);
+      while (skip && p < fl_end) {
+        ++entry_idx;
         const uint32_t b1 = T.b[p + 1];
-        if (b1 < 0x80) { p += 2 + b1; continue; }
-        ++p;
-        uint32_t el;
-        if (!t_len(T, p, fl_end, el)) { bad = true; break; }
-        p += el;
-        continue;
+        if (b1 < 0x80) p += 2 + b1;
+        else {
+          uint32_t q = p + 1, el;
+          if (!t_len(T, q, fl_end, el)) { bad = true; break; }
+          p = q + el;
+        }
+        --skip;
       }
+      if (bad || p >= fl_end) break;
+      ++entry_idx;                                           // the entry this warp owns
       uint32_t elen, klen, vlen;
       if (T.b[p] != 0x0A) { bad = true; break; }
       ++p;
