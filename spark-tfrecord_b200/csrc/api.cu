@@ -293,7 +293,7 @@ struct tfr_decoder {
   cudaStream_t stream = nullptr;
   DevSchemaBuf dsch;
   // reusable device scratch
-  DevBuf in, chunks, chunk_base, rec_off, status, valid8, cnt, src, cflag, tsum, scan_scratch, ptr_tables, small;
+  DevBuf in, chunks, chunk_base, chunk_cnt, k1_tsum, rec_off, status, valid8, cnt, src, cflag, tsum, scan_scratch, ptr_tables, small;
   // pinned host
   void* staging = nullptr; size_t staging_cap = 0;
   HostStats* h_stats = nullptr;
@@ -310,6 +310,7 @@ struct tfr_decoder {
   std::vector<int32_t> spec_len;
   DevBuf uniform_dev;
   int32_t* h_uniform = nullptr;         // pinned
+  void* h_k1 = nullptr;                 // pinned, 16 bytes
   // profiling (bench.py): CUDA events around the stages
   bool profiling = false;
   struct Span { int stage; cudaEvent_t a, b; };
@@ -370,6 +371,7 @@ extern "C" int32_t tfr_decoder_create(const tfr_schema* schema, int32_t device, 
     if (getenv("TFR_DISABLE_SPECULATION")) d->spec_state = -1;
     d->spec_len.assign(std::max(1, d->schema.n_var), -1);
     CUDA_TRY(cudaHostAlloc((void**)&d->h_uniform, std::max<size_t>(1, d->schema.n_var) * 4, cudaHostAllocDefault));
+    CUDA_TRY(cudaHostAlloc(&d->h_k1, 64, cudaHostAllocDefault));
   }
   CUDA_TRY(cudaHostAlloc((void**)&d->h_stats, sizeof(HostStats), cudaHostAllocDefault));
   size_t nt = (size_t)d->schema.n_cnt * 2 + d->schema.fields.size() + 8;
@@ -383,13 +385,14 @@ static void decoder_unref(tfr_decoder* d) {
   if (d->refs.fetch_sub(1) != 1) return;
   cudaSetDevice(d->device);
   cudaStreamSynchronize(d->stream);
-  for (DevBuf* b : {&d->in, &d->chunks, &d->chunk_base, &d->rec_off, &d->status, &d->valid8, &d->cnt, &d->src, &d->cflag, &d->tsum,
+  for (DevBuf* b : {&d->in, &d->chunks, &d->chunk_base, &d->chunk_cnt, &d->k1_tsum, &d->rec_off, &d->status, &d->valid8, &d->cnt, &d->src, &d->cflag, &d->tsum,
                     &d->scan_scratch, &d->ptr_tables, &d->small, &d->uniform_dev})
     b->release();
   d->dsch.free_all();
   if (d->staging) cudaFreeHost(d->staging);
   cudaFreeHost(d->h_stats); cudaFreeHost(d->h_totals);
   if (d->h_uniform) cudaFreeHost(d->h_uniform);
+  if (d->h_k1) cudaFreeHost(d->h_k1);
   if (d->h_ptr_tables) cudaFreeHost(d->h_ptr_tables);
   d->host_pool.release_all();
   d->dev_pool.release_all();
@@ -534,9 +537,8 @@ static int32_t ensure_rec_off(DecodeCtx& C) {
   if (C.rec_off_ready) return TFR_OK;
   tfr_decoder* d = C.d;
   TRY(d->rec_off.ensure(((size_t)C.n + 1) * 4));
-  uint32_t grid = std::min<uint32_t>((C.n_chunks + 7) / 8, (uint32_t)d->ctx->sm_count * 8);
   d->span_begin(0);
-  frame_emit_kernel<<<grid, 256, 0, C.st>>>(C.d_data, (const ChunkInfo*)d->chunks.p, (const uint32_t*)d->chunk_base.p, C.n_chunks,
+  frame_emit_kernel<<<(C.n_chunks + 127) / 128, 128, 0, C.st>>>(C.d_data, (const ChunkInfo*)d->chunks.p, (const uint32_t*)d->chunk_base.p, C.n_chunks,
                                             (const FrameResult*)d->small.p, (uint32_t*)d->rec_off.p);
   d->span_end(1);
   C.rec_off_ready = true;
@@ -696,14 +698,28 @@ static int32_t decode_impl(tfr_decoder* d, const void* data, size_t nbytes, int3
     FrameResult init{}; init.first_bad = 0xffffffffu;
     d->h_stats->frame = init;
     CUDA_TRY(cudaMemcpyAsync(d_fr, &d->h_stats->frame, sizeof(FrameResult), cudaMemcpyHostToDevice, st));
-    uint32_t grid = std::min<uint32_t>((C.n_chunks + 7) / 8, (uint32_t)d->ctx->sm_count * 8);
     const uint32_t v = verify_headers ? C.verify : 0u;
+    TRY(d->chunk_cnt.ensure(((size_t)C.n_chunks + 1) * 4));
+    const uint32_t kt = (C.n_chunks + SCAN_TILE - 1) / SCAN_TILE;
+    TRY(d->k1_tsum.ensure(((size_t)kt + 2) * 8 + 64));
+    uint64_t* tsum = (uint64_t*)d->k1_tsum.p; uint64_t* traw = tsum + kt;
+    uint32_t* d_stop = (uint32_t*)((uint8_t*)d->small.p + 128);                 // [0] stop chunk, [1] scratch overflow flag, [2..3] chunk_base pointer
+    uint32_t stop_init[2] = {0xffffffffu, 0};
+    memcpy(d->h_k1, stop_init, 8);
+    void* cb = d->chunk_base.p; memcpy((uint8_t*)d->h_k1 + 8, &cb, sizeof(void*));
+    CUDA_TRY(cudaMemcpyAsync(d_stop, d->h_k1, 16, cudaMemcpyHostToDevice, st));
     d->span_begin(0);
-    frame_scan_kernel<<<grid, 256, 0, st>>>(C.d_data, (uint32_t)nbytes, C.chunk_bytes, C.n_chunks, v, d->ctx->d_tabs, (ChunkInfo*)d->chunks.p, d_fr);
+    frame_scan_kernel<<<(C.n_chunks + 127) / 128, 128, 0, st>>>(C.d_data, (uint32_t)nbytes, C.chunk_bytes, C.n_chunks, v, d->ctx->d_tabs, (ChunkInfo*)d->chunks.p,
+                                                             (uint32_t*)d->chunk_cnt.p, d_fr);
     frame_check_kernel<<<(C.n_chunks + 255) / 256, 256, 0, st>>>((const ChunkInfo*)d->chunks.p, C.n_chunks, d_fr);
-    frame_repair_kernel<<<1, 32, 0, st>>>(C.d_data, (uint32_t)nbytes, C.chunk_bytes, C.n_chunks, v, d->ctx->d_tabs, (ChunkInfo*)d->chunks.p, d_fr);
-    frame_finish_kernel<<<1, 1024, 0, st>>>((const ChunkInfo*)d->chunks.p, C.n_chunks, (uint32_t)nbytes, (uint32_t*)d->chunk_base.p, d_fr);
-    d->span_end(4);
+    frame_repair_kernel<<<1, 32, 0, st>>>(C.d_data, (uint32_t)nbytes, C.chunk_bytes, C.n_chunks, v, d->ctx->d_tabs, (ChunkInfo*)d->chunks.p,
+                                          (uint32_t*)d->chunk_cnt.p, d_fr);
+    frame_stop_kernel<<<(C.n_chunks + 255) / 256, 256, 0, st>>>((const ChunkInfo*)d->chunks.p, C.n_chunks, d_stop);
+    scan_tile_sums_kernel<<<dim3(kt, 1), SCAN_THREADS, 0, st>>>((const uint32_t*)d->chunk_cnt.p, C.n_chunks, kt, tsum);
+    scan_tile_bases_kernel<<<1, 1024, 0, st>>>(tsum, kt, traw, d_stop + 1);
+    scan_apply_kernel<<<dim3(kt, 1), SCAN_THREADS, 0, st>>>((const uint32_t*)d->chunk_cnt.p, C.n_chunks, kt, tsum, traw, (int32_t* const*)(d_stop + 2));
+    frame_finish_kernel<<<1, 32, 0, st>>>((const ChunkInfo*)d->chunks.p, C.n_chunks, (uint32_t)nbytes, (const uint32_t*)d->chunk_base.p, d_stop, d_fr);
+    d->span_end(8);
     CUDA_TRY(cudaMemcpyAsync(&d->h_stats->frame, d_fr, sizeof(FrameResult), cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));                       // sync #1: number of records
     CUDA_TRY(cudaGetLastError());

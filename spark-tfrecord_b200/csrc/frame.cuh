@@ -69,49 +69,63 @@ __device__ __forceinline__ uint32_t frame_chain(const uint32_t* t0, const uint8_
   return q == nbytes ? FS_EOF : FS_LEFT;
 }
 
-// one warp per chunk
-__global__ void __launch_bounds__(256) frame_scan_kernel(const uint8_t* __restrict__ data, uint32_t nbytes, uint32_t chunk_bytes,
+// one THREAD per chunk: the walk is a DRAM-latency-bound pointer chase, so the win is chains in flight, not
+// lanes per chain.  The candidate search streams aligned words (one load per 4 candidate offsets) and tests
+// the cheapest condition first (upper half of the length == 0).
+__global__ void __launch_bounds__(128) frame_scan_kernel(const uint8_t* __restrict__ data, uint32_t nbytes, uint32_t chunk_bytes,
                                                          uint32_t n_chunks, uint32_t verify, const CrcTables* __restrict__ tabs,
-                                                         ChunkInfo* __restrict__ chunks, FrameResult* __restrict__ res) {
+                                                         ChunkInfo* __restrict__ chunks, uint32_t* __restrict__ chunk_cnt,
+                                                         FrameResult* __restrict__ res) {
   __shared__ uint32_t t0[256];
   for (int i = threadIdx.x; i < 256; i += blockDim.x) t0[i] = tabs->t0[i];
   __syncthreads();
-  const uint32_t lane = threadIdx.x & 31;
-  const uint32_t warps_per_block = blockDim.x >> 5;
-  for (uint32_t k = blockIdx.x * warps_per_block + (threadIdx.x >> 5); k < n_chunks; k += gridDim.x * warps_per_block) {
-    const uint32_t cs = k * chunk_bytes;
-    const uint32_t ce = (nbytes - cs > chunk_bytes) ? cs + chunk_bytes : nbytes;
-    uint32_t first = 0xffffffffu;
-    if (k == 0) first = 0;
-    else {
-      // candidate p is plausible iff its 12-byte header is inside the buffer, the stored CRC matches the
-      // masked CRC-32C of the 8 length bytes, and the length fits an int32 (false positive 2^-32 per byte
-      // on random data; adversarial data is caught by frame_check and fixed by frame_repair)
-      for (uint32_t p0 = cs; p0 < ce && first == 0xffffffffu; p0 += 32) {
-        uint32_t p = p0 + lane;
-        bool hit = false;
-        if (p < ce && nbytes - p >= 12) {
-          // cheapest test first: the upper half of a plausible length is zero (one load instead of three)
-          uint32_t hi = load_u32_unaligned(data + p + 4);
-          if (hi == 0) {
-            uint32_t lo = load_u32_unaligned(data + p);
-            if (lo <= 0x7fffffffu) hit = crc_mask(crc_u64(t0, lo, hi)) == load_u32_unaligned(data + p + 8);
+  const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n_chunks) return;
+  const uint32_t cs = k * chunk_bytes;
+  const uint32_t ce = (nbytes - cs > chunk_bytes) ? cs + chunk_bytes : nbytes;
+  uint32_t first = 0xffffffffu;
+  if (k == 0) first = 0;
+  else if (nbytes - cs >= 12) {
+    // candidate p is plausible iff its 12-byte header is inside the buffer, the stored CRC matches the masked
+    // CRC-32C of the 8 length bytes, and the length fits an int32 (false positive 2^-32 per byte on random
+    // data; adversarial data is caught by frame_check and fixed by frame_repair)
+    const uint32_t last = min(ce - 1, nbytes - 12);                        // last candidate offset
+    const uint32_t* W = reinterpret_cast<const uint32_t*>(data + cs);        // chunk starts are 4-byte aligned relative to data
+    const uint32_t misalign = (uint32_t)(reinterpret_cast<uintptr_t>(data) & 3);
+    if (misalign == 0) {
+      uint32_t w0 = W[0], w1 = W[1], w2 = W[2];
+      for (uint32_t i = 0; cs + 4 * i <= last && first == 0xffffffffu; ++i) {
+        const uint32_t w3 = W[i + 3];                                         // <= 3 words past the candidate: inside the padded buffer
+#pragma unroll
+        for (uint32_t b = 0; b < 4; ++b) {
+          const uint32_t hi = b ? __funnelshift_r(w1, w2, 8 * b) : w1;
+          if (hi == 0 && first == 0xffffffffu) {
+            const uint32_t p = cs + 4 * i + b;
+            const uint32_t lo = b ? __funnelshift_r(w0, w1, 8 * b) : w0;
+            const uint32_t crc = b ? __funnelshift_r(w2, w3, 8 * b) : w2;
+            if (p <= last && lo <= 0x7fffffffu && crc_mask(crc_u64(t0, lo, 0)) == crc) first = p;
           }
         }
-        uint32_t m = __ballot_sync(FULLMASK, hit);
-        if (m) first = p0 + (uint32_t)(__ffs(m) - 1);
+        w0 = w1; w1 = w2; w2 = w3;
+      }
+    } else {
+      for (uint32_t p = cs; p <= last; ++p) {
+        if (load_u32_unaligned(data + p + 4) != 0) continue;
+        const uint32_t lo = load_u32_unaligned(data + p);
+        if (lo <= 0x7fffffffu && crc_mask(crc_u64(t0, lo, 0)) == load_u32_unaligned(data + p + 8)) { first = p; break; }
       }
     }
-    ChunkInfo ci;
-    ci.first = first; ci.end = first; ci.count = 0; ci.stop = FS_NONE;
-    if (first != 0xffffffffu) {
-      uint32_t q = first, cnt = 0, mx = 0;
-      ci.stop = frame_chain(t0, data, nbytes, ce, verify != 0, q, cnt, mx);   // uniform across the warp
-      ci.end = q; ci.count = cnt;
-      if (lane == 0 && mx) atomicMax(&res->max_len, mx);                  // a false candidate can only enlarge the bound
-    }
-    if (lane == 0) chunks[k] = ci;
   }
+  ChunkInfo ci;
+  ci.first = first; ci.end = first; ci.count = 0; ci.stop = FS_NONE;
+  if (first != 0xffffffffu) {
+    uint32_t q = first, cnt = 0, mx = 0;
+    ci.stop = frame_chain(t0, data, nbytes, ce, verify != 0, q, cnt, mx);
+    ci.end = q; ci.count = cnt;
+    if (mx) atomicMax(&res->max_len, mx);                                  // a false candidate can only enlarge the bound
+  }
+  chunks[k] = ci;
+  chunk_cnt[k] = ci.count;
 }
 
 // link check: chunk k (k >= 1) is consistent iff the previous chunk's chain left exactly onto its guess
@@ -129,7 +143,7 @@ __global__ void frame_check_kernel(const ChunkInfo* __restrict__ chunks, uint32_
 // Starts at the first broken link and re-chains until the speculation re-synchronises.
 __global__ void frame_repair_kernel(const uint8_t* __restrict__ data, uint32_t nbytes, uint32_t chunk_bytes, uint32_t n_chunks,
                                     uint32_t verify, const CrcTables* __restrict__ tabs, ChunkInfo* __restrict__ chunks,
-                                    FrameResult* __restrict__ res) {
+                                    uint32_t* __restrict__ chunk_cnt, FrameResult* __restrict__ res) {
   __shared__ uint32_t t0[256];
   for (int i = threadIdx.x; i < 256; i += blockDim.x) t0[i] = tabs->t0[i];
   __syncthreads();
@@ -144,7 +158,7 @@ __global__ void frame_repair_kernel(const uint8_t* __restrict__ data, uint32_t n
     const uint32_t ce = (nbytes - cs > chunk_bytes) ? cs + chunk_bytes : nbytes;
     ChunkInfo ci = chunks[k];
     if (stopped || F >= ce) {           // no record starts in this chunk
-      if (ci.first != 0xffffffffu || ci.count) { ci.first = 0xffffffffu; ci.count = 0; ci.stop = FS_NONE; ci.end = F; chunks[k] = ci; ++repairs; }
+      if (ci.first != 0xffffffffu || ci.count) { ci.first = 0xffffffffu; ci.count = 0; ci.stop = FS_NONE; ci.end = F; chunks[k] = ci; chunk_cnt[k] = 0; ++repairs; }
       continue;
     }
     if (ci.first == F) {                // speculation is right from here on: re-synchronised
@@ -160,85 +174,46 @@ __global__ void frame_repair_kernel(const uint8_t* __restrict__ data, uint32_t n
     ci.stop = frame_chain(t0, data, nbytes, ce, verify != 0, q, cnt, mx);
     if (mx) atomicMax(&res->max_len, mx);
     ci.end = q; ci.count = cnt;
-    chunks[k] = ci; ++repairs;
+    chunks[k] = ci; chunk_cnt[k] = cnt; ++repairs;
     if (ci.stop != FS_LEFT) stopped = true; else F = q;
   }
   res->repairs = repairs;
 }
 
-// exclusive prefix sum of chunk counts (single block) + stream stop reason
-__global__ void __launch_bounds__(1024) frame_finish_kernel(const ChunkInfo* __restrict__ chunks, uint32_t n_chunks, uint32_t nbytes,
-                                                            uint32_t* __restrict__ chunk_base, FrameResult* __restrict__ res) {
-  __shared__ uint32_t warp_sums[32];
-  __shared__ uint32_t carry;
-  __shared__ uint32_t stop_chunk;
-  if (threadIdx.x == 0) { carry = 0; stop_chunk = 0xffffffffu; }
-  __syncthreads();
-  const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  for (uint32_t base = 0; base < n_chunks; base += blockDim.x) {
-    uint32_t k = base + threadIdx.x;
-    uint32_t c = 0;
-    if (k < n_chunks) {
-      ChunkInfo ci = chunks[k];
-      c = ci.count;
-      if (ci.first != 0xffffffffu && ci.stop != FS_LEFT) atomicMin(&stop_chunk, k);
-    }
-    uint32_t x = c;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync(FULLMASK, x, o); if (lane >= (uint32_t)o) x += y; }
-    if (lane == 31) warp_sums[wid] = x;
-    __syncthreads();
-    if (wid == 0) {
-      uint32_t s = warp_sums[lane];
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync(FULLMASK, s, o); if (lane >= (uint32_t)o) s += y; }
-      warp_sums[lane] = s;
-    }
-    __syncthreads();
-    uint32_t excl = x - c + (wid ? warp_sums[wid - 1] : 0) + carry;
-    if (k < n_chunks) chunk_base[k] = excl;
-    __syncthreads();
-    if (threadIdx.x == blockDim.x - 1) carry = excl + c;
-    __syncthreads();
-  }
-  if (threadIdx.x == 0) {
-    if (n_chunks == 0) { res->n_records = 0; res->stop = FS_EOF; res->stop_pos = 0; return; }
-    // records that start after the stop chunk do not exist (repair cleared them); the stop chunk is the
-    // first (and only) chunk with a non-LEFT stop
-    uint32_t sc = stop_chunk;
-    if (sc == 0xffffffffu) {   // cannot happen for nbytes > 0: the last live chunk always stops
-      res->n_records = carry; res->stop = FS_EOF; res->stop_pos = nbytes; return;
-    }
-    ChunkInfo ci = chunks[sc];
-    res->n_records = chunk_base[sc] + ci.count;
-    res->stop = ci.stop; res->stop_pos = ci.end;
-    chunk_base[n_chunks] = carry;
-  }
+// stream stop reason + record count (the chunk counts are prefix-summed by scan.cuh's kernels into chunk_base)
+__global__ void frame_stop_kernel(const ChunkInfo* __restrict__ chunks, uint32_t n_chunks, uint32_t* __restrict__ stop_chunk) {
+  uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n_chunks) return;
+  ChunkInfo ci = chunks[k];
+  if (ci.first != 0xffffffffu && ci.stop != FS_LEFT) atomicMin(stop_chunk, k);
+}
+__global__ void frame_finish_kernel(const ChunkInfo* __restrict__ chunks, uint32_t n_chunks, uint32_t nbytes,
+                                    const uint32_t* __restrict__ chunk_base, const uint32_t* __restrict__ stop_chunk, FrameResult* __restrict__ res) {
+  if (threadIdx.x || blockIdx.x) return;
+  // records that start after the stop chunk do not exist (repair cleared them); the stop chunk is the first (and only)
+  // chunk with a non-LEFT stop
+  uint32_t sc = *stop_chunk;
+  if (n_chunks == 0) { res->n_records = 0; res->stop = FS_EOF; res->stop_pos = 0; return; }
+  if (sc == 0xffffffffu) { res->n_records = chunk_base[n_chunks]; res->stop = FS_EOF; res->stop_pos = nbytes; return; }   // cannot happen for nbytes > 0
+  ChunkInfo ci = chunks[sc];
+  res->n_records = chunk_base[sc] + ci.count;
+  res->stop = ci.stop; res->stop_pos = ci.end;
 }
 
-// re-walk each chunk and write the record offsets; rec_off[n] = stop_pos
-__global__ void __launch_bounds__(256) frame_emit_kernel(const uint8_t* __restrict__ data, const ChunkInfo* __restrict__ chunks,
+// re-walk each chunk (one thread per chunk) and write the record offsets; rec_off[n] = stop_pos
+__global__ void __launch_bounds__(128) frame_emit_kernel(const uint8_t* __restrict__ data, const ChunkInfo* __restrict__ chunks,
                                                          const uint32_t* __restrict__ chunk_base, uint32_t n_chunks,
                                                          const FrameResult* __restrict__ res, uint32_t* __restrict__ rec_off) {
-  const uint32_t lane = threadIdx.x & 31;
-  const uint32_t warps_per_block = blockDim.x >> 5;
   const uint32_t n = res->n_records;
-  if (blockIdx.x == 0 && threadIdx.x == 0) rec_off[n] = res->stop_pos;
-  for (uint32_t k = blockIdx.x * warps_per_block + (threadIdx.x >> 5); k < n_chunks; k += gridDim.x * warps_per_block) {
-    ChunkInfo ci = chunks[k];
-    if (ci.first == 0xffffffffu || ci.count == 0) continue;
-    uint32_t base = chunk_base[k];
-    if (base >= n) continue;
-    uint32_t q = ci.first;
-    // lanes take turns holding the offsets so the stores are coalesced 32 at a time
-    for (uint32_t i0 = 0; i0 < ci.count; i0 += 32) {
-      uint32_t mine = 0;
-      uint32_t lim = min(32u, ci.count - i0);
-      for (uint32_t j = 0; j < lim; ++j) {
-        if (lane == j) mine = q;
-        q += 16 + load_u32_unaligned(data + q);
-      }
-      if (lane < lim && base + i0 + lane < n) rec_off[base + i0 + lane] = mine;
-    }
+  const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k == 0) rec_off[n] = res->stop_pos;
+  if (k >= n_chunks) return;
+  ChunkInfo ci = chunks[k];
+  if (ci.first == 0xffffffffu || ci.count == 0) return;
+  const uint32_t base = chunk_base[k];
+  uint32_t q = ci.first;
+  for (uint32_t i = 0; i < ci.count && base + i < n; ++i) {
+    rec_off[base + i] = q;
+    q += 16 + load_u32_unaligned(data + q);
   }
 }
