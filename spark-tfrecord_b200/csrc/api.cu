@@ -293,7 +293,7 @@ struct tfr_decoder {
   cudaStream_t stream = nullptr;
   DevSchemaBuf dsch;
   // reusable device scratch
-  DevBuf in, chunks, chunk_base, chunk_cnt, k1_tsum, rec_off, status, valid8, cnt, src, cflag, tsum, scan_scratch, ptr_tables, small;
+  DevBuf in, chunks, chunk_base, chunk_cnt, k1_tsum, k1_first, rec_off, status, valid8, cnt, src, cflag, tsum, scan_scratch, ptr_tables, small;
   // pinned host
   void* staging = nullptr; size_t staging_cap = 0;
   HostStats* h_stats = nullptr;
@@ -385,7 +385,7 @@ static void decoder_unref(tfr_decoder* d) {
   if (d->refs.fetch_sub(1) != 1) return;
   cudaSetDevice(d->device);
   cudaStreamSynchronize(d->stream);
-  for (DevBuf* b : {&d->in, &d->chunks, &d->chunk_base, &d->chunk_cnt, &d->k1_tsum, &d->rec_off, &d->status, &d->valid8, &d->cnt, &d->src, &d->cflag, &d->tsum,
+  for (DevBuf* b : {&d->in, &d->chunks, &d->chunk_base, &d->chunk_cnt, &d->k1_tsum, &d->k1_first, &d->rec_off, &d->status, &d->valid8, &d->cnt, &d->src, &d->cflag, &d->tsum,
                     &d->scan_scratch, &d->ptr_tables, &d->small, &d->uniform_dev})
     b->release();
   d->dsch.free_all();
@@ -709,8 +709,11 @@ static int32_t decode_impl(tfr_decoder* d, const void* data, size_t nbytes, int3
     void* cb = d->chunk_base.p; memcpy((uint8_t*)d->h_k1 + 8, &cb, sizeof(void*));
     CUDA_TRY(cudaMemcpyAsync(d_stop, d->h_k1, 16, cudaMemcpyHostToDevice, st));
     d->span_begin(0);
-    frame_scan_kernel<<<(C.n_chunks + 127) / 128, 128, 0, st>>>(C.d_data, (uint32_t)nbytes, C.chunk_bytes, C.n_chunks, v, d->ctx->d_tabs, (ChunkInfo*)d->chunks.p,
-                                                             (uint32_t*)d->chunk_cnt.p, d_fr);
+    TRY(d->k1_first.ensure(((size_t)C.n_chunks + 1) * 4));
+    frame_search_kernel<<<std::min<uint32_t>((C.n_chunks + 7) / 8, (uint32_t)d->ctx->sm_count * 8), 256, 0, st>>>(C.d_data, (uint32_t)nbytes, C.chunk_bytes, C.n_chunks,
+                                                                                                             d->ctx->d_tabs, (uint32_t*)d->k1_first.p);
+    frame_scan_kernel<<<(C.n_chunks + 127) / 128, 128, 0, st>>>(C.d_data, (uint32_t)nbytes, C.chunk_bytes, C.n_chunks, v, d->ctx->d_tabs, (const uint32_t*)d->k1_first.p,
+                                                             (ChunkInfo*)d->chunks.p, (uint32_t*)d->chunk_cnt.p, d_fr);
     frame_check_kernel<<<(C.n_chunks + 255) / 256, 256, 0, st>>>((const ChunkInfo*)d->chunks.p, C.n_chunks, d_fr);
     frame_repair_kernel<<<1, 32, 0, st>>>(C.d_data, (uint32_t)nbytes, C.chunk_bytes, C.n_chunks, v, d->ctx->d_tabs, (ChunkInfo*)d->chunks.p,
                                           (uint32_t*)d->chunk_cnt.p, d_fr);
@@ -719,7 +722,7 @@ static int32_t decode_impl(tfr_decoder* d, const void* data, size_t nbytes, int3
     scan_tile_bases_kernel<<<1, 1024, 0, st>>>(tsum, kt, traw, d_stop + 1);
     scan_apply_kernel<<<dim3(kt, 1), SCAN_THREADS, 0, st>>>((const uint32_t*)d->chunk_cnt.p, C.n_chunks, kt, tsum, traw, (int32_t* const*)(d_stop + 2));
     frame_finish_kernel<<<1, 32, 0, st>>>((const ChunkInfo*)d->chunks.p, C.n_chunks, (uint32_t)nbytes, (const uint32_t*)d->chunk_base.p, d_stop, d_fr);
-    d->span_end(8);
+    d->span_end(9);
     CUDA_TRY(cudaMemcpyAsync(&d->h_stats->frame, d_fr, sizeof(FrameResult), cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));                       // sync #1: number of records
     CUDA_TRY(cudaGetLastError());

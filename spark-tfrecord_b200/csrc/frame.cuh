@@ -69,13 +69,49 @@ __device__ __forceinline__ uint32_t frame_chain(const uint32_t* t0, const uint8_
   return q == nbytes ? FS_EOF : FS_LEFT;
 }
 
-// one THREAD per chunk: the walk is a DRAM-latency-bound pointer chase, so the win is chains in flight, not
-// lanes per chain.  The candidate search streams aligned words (one load per 4 candidate offsets) and tests
-// the cheapest condition first (upper half of the length == 0).
+// K1a -- candidate search, one WARP per chunk: 32 consecutive candidate offsets per step (coalesced: the warp's
+// loads fall into one or two sectors), cheapest condition first (the upper half of a plausible length is zero),
+// __ballot_sync picks the first hit.  The first 2 KiB of the chunk are prefetched by 16 lanes up front so the
+// steps hit L1 instead of paying one dependent DRAM miss per 128-byte line.
+__global__ void __launch_bounds__(256) frame_search_kernel(const uint8_t* __restrict__ data, uint32_t nbytes, uint32_t chunk_bytes,
+                                                           uint32_t n_chunks, const CrcTables* __restrict__ tabs, uint32_t* __restrict__ first_out) {
+  __shared__ uint32_t t0[256];
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) t0[i] = tabs->t0[i];
+  __syncthreads();
+  const uint32_t lane = threadIdx.x & 31;
+  const uint32_t warps_per_block = blockDim.x >> 5;
+  for (uint32_t k = blockIdx.x * warps_per_block + (threadIdx.x >> 5); k < n_chunks; k += gridDim.x * warps_per_block) {
+    const uint32_t cs = k * chunk_bytes;
+    const uint32_t ce = (nbytes - cs > chunk_bytes) ? cs + chunk_bytes : nbytes;
+    uint32_t first = 0xffffffffu;
+    if (k == 0) first = 0;
+    else if (nbytes - cs >= 12) {
+      // a candidate p is plausible iff its 12-byte header is inside the buffer, the stored CRC matches the masked
+      // CRC-32C of the 8 length bytes and the length fits an int32 (false positive 2^-32 per byte on random data;
+      // adversarial data is caught by frame_check and fixed by frame_repair)
+      const uint32_t last = min(ce - 1, nbytes - 12);
+      for (uint32_t p0 = cs; p0 <= last && first == 0xffffffffu; p0 += 32) {
+        if (((p0 - cs) & 2047u) == 0 && lane < 17 && p0 + 128u * lane < nbytes)
+          asm volatile("prefetch.global.L1 [%0];" ::"l"(data + p0 + 128u * lane));
+        const uint32_t p = p0 + lane;
+        bool hit = false;
+        if (p <= last && load_u32_unaligned(data + p + 4) == 0) {
+          const uint32_t lo = load_u32_unaligned(data + p);
+          hit = lo <= 0x7fffffffu && crc_mask(crc_u64(t0, lo, 0)) == load_u32_unaligned(data + p + 8);
+        }
+        const uint32_t m = __ballot_sync(FULLMASK, hit);
+        if (m) first = p0 + (uint32_t)(__ffs(m) - 1);
+      }
+    }
+    if (lane == 0) first_out[k] = first;
+  }
+}
+
+// K1b -- chain walk, one THREAD per chunk: a DRAM-latency-bound pointer chase, so the win is chains in flight.
 __global__ void __launch_bounds__(128) frame_scan_kernel(const uint8_t* __restrict__ data, uint32_t nbytes, uint32_t chunk_bytes,
                                                          uint32_t n_chunks, uint32_t verify, const CrcTables* __restrict__ tabs,
-                                                         ChunkInfo* __restrict__ chunks, uint32_t* __restrict__ chunk_cnt,
-                                                         FrameResult* __restrict__ res) {
+                                                         const uint32_t* __restrict__ first_in, ChunkInfo* __restrict__ chunks,
+                                                         uint32_t* __restrict__ chunk_cnt, FrameResult* __restrict__ res) {
   __shared__ uint32_t t0[256];
   for (int i = threadIdx.x; i < 256; i += blockDim.x) t0[i] = tabs->t0[i];
   __syncthreads();
@@ -83,39 +119,7 @@ __global__ void __launch_bounds__(128) frame_scan_kernel(const uint8_t* __restri
   if (k >= n_chunks) return;
   const uint32_t cs = k * chunk_bytes;
   const uint32_t ce = (nbytes - cs > chunk_bytes) ? cs + chunk_bytes : nbytes;
-  uint32_t first = 0xffffffffu;
-  if (k == 0) first = 0;
-  else if (nbytes - cs >= 12) {
-    // candidate p is plausible iff its 12-byte header is inside the buffer, the stored CRC matches the masked
-    // CRC-32C of the 8 length bytes, and the length fits an int32 (false positive 2^-32 per byte on random
-    // data; adversarial data is caught by frame_check and fixed by frame_repair)
-    const uint32_t last = min(ce - 1, nbytes - 12);                        // last candidate offset
-    const uint32_t* W = reinterpret_cast<const uint32_t*>(data + cs);        // chunk starts are 4-byte aligned relative to data
-    const uint32_t misalign = (uint32_t)(reinterpret_cast<uintptr_t>(data) & 3);
-    if (misalign == 0) {
-      uint32_t w0 = W[0], w1 = W[1], w2 = W[2];
-      for (uint32_t i = 0; cs + 4 * i <= last && first == 0xffffffffu; ++i) {
-        const uint32_t w3 = W[i + 3];                                         // <= 3 words past the candidate: inside the padded buffer
-#pragma unroll
-        for (uint32_t b = 0; b < 4; ++b) {
-          const uint32_t hi = b ? __funnelshift_r(w1, w2, 8 * b) : w1;
-          if (hi == 0 && first == 0xffffffffu) {
-            const uint32_t p = cs + 4 * i + b;
-            const uint32_t lo = b ? __funnelshift_r(w0, w1, 8 * b) : w0;
-            const uint32_t crc = b ? __funnelshift_r(w2, w3, 8 * b) : w2;
-            if (p <= last && lo <= 0x7fffffffu && crc_mask(crc_u64(t0, lo, 0)) == crc) first = p;
-          }
-        }
-        w0 = w1; w1 = w2; w2 = w3;
-      }
-    } else {
-      for (uint32_t p = cs; p <= last; ++p) {
-        if (load_u32_unaligned(data + p + 4) != 0) continue;
-        const uint32_t lo = load_u32_unaligned(data + p);
-        if (lo <= 0x7fffffffu && crc_mask(crc_u64(t0, lo, 0)) == load_u32_unaligned(data + p + 8)) { first = p; break; }
-      }
-    }
-  }
+  const uint32_t first = first_in[k];
   ChunkInfo ci;
   ci.first = first; ci.end = first; ci.count = 0; ci.stop = FS_NONE;
   if (first != 0xffffffffu) {
