@@ -293,7 +293,7 @@ struct tfr_decoder {
   cudaStream_t stream = nullptr;
   DevSchemaBuf dsch;
   // reusable device scratch
-  DevBuf in, chunks, chunk_base, chunk_cnt, k1_tsum, k1_first, rec_off, status, valid8, cnt, src, cflag, tsum, scan_scratch, ptr_tables, small;
+  DevBuf in, chunks, chunk_base, chunk_cnt, k1_tsum, k1_first, k1_stage, rec_off, status, valid8, cnt, src, cflag, tsum, scan_scratch, ptr_tables, small;
   // pinned host
   void* staging = nullptr; size_t staging_cap = 0;
   HostStats* h_stats = nullptr;
@@ -385,7 +385,7 @@ static void decoder_unref(tfr_decoder* d) {
   if (d->refs.fetch_sub(1) != 1) return;
   cudaSetDevice(d->device);
   cudaStreamSynchronize(d->stream);
-  for (DevBuf* b : {&d->in, &d->chunks, &d->chunk_base, &d->chunk_cnt, &d->k1_tsum, &d->k1_first, &d->rec_off, &d->status, &d->valid8, &d->cnt, &d->src, &d->cflag, &d->tsum,
+  for (DevBuf* b : {&d->in, &d->chunks, &d->chunk_base, &d->chunk_cnt, &d->k1_tsum, &d->k1_first, &d->k1_stage, &d->rec_off, &d->status, &d->valid8, &d->cnt, &d->src, &d->cflag, &d->tsum,
                     &d->scan_scratch, &d->ptr_tables, &d->small, &d->uniform_dev})
     b->release();
   d->dsch.free_all();
@@ -450,9 +450,11 @@ static int32_t frame_stop_to_error(uint32_t stop, bool is_final) {
 
 static uint32_t pick_chunk_bytes(size_t nbytes, int sm_count) {
   // enough chunks to give every resident warp work, large enough to amortise the candidate search
+  // the frame index costs one candidate search per chunk (the dominant part) plus one dependent DRAM hop per
+  // record: aim for about one chunk per resident warp
   size_t want = (size_t)sm_count * 64;
   size_t c = 4096;
-  while (c < 65536 && nbytes / c > want * 4) c <<= 1;
+  while (c < 262144 && nbytes / c > want) c <<= 1;
   return (uint32_t)c;
 }
 
@@ -538,8 +540,8 @@ static int32_t ensure_rec_off(DecodeCtx& C) {
   tfr_decoder* d = C.d;
   TRY(d->rec_off.ensure(((size_t)C.n + 1) * 4));
   d->span_begin(0);
-  frame_emit_kernel<<<(C.n_chunks + 127) / 128, 128, 0, C.st>>>(C.d_data, (const ChunkInfo*)d->chunks.p, (const uint32_t*)d->chunk_base.p, C.n_chunks,
-                                            (const FrameResult*)d->small.p, (uint32_t*)d->rec_off.p);
+  frame_emit_kernel<<<(C.n_chunks * FRAME_EMIT_LANES + 255) / 256, 256, 0, C.st>>>(C.d_data, (const ChunkInfo*)d->chunks.p, (const uint32_t*)d->chunk_base.p, C.n_chunks,
+                                                                                  (const uint32_t*)d->k1_stage.p, (const FrameResult*)d->small.p, (uint32_t*)d->rec_off.p);
   d->span_end(1);
   C.rec_off_ready = true;
   return TFR_OK;
@@ -710,13 +712,14 @@ static int32_t decode_impl(tfr_decoder* d, const void* data, size_t nbytes, int3
     CUDA_TRY(cudaMemcpyAsync(d_stop, d->h_k1, 16, cudaMemcpyHostToDevice, st));
     d->span_begin(0);
     TRY(d->k1_first.ensure(((size_t)C.n_chunks + 1) * 4));
+    TRY(d->k1_stage.ensure((size_t)C.n_chunks * FRAME_STAGE * 4 + 64));
     frame_search_kernel<<<std::min<uint32_t>((C.n_chunks + 7) / 8, (uint32_t)d->ctx->sm_count * 8), 256, 0, st>>>(C.d_data, (uint32_t)nbytes, C.chunk_bytes, C.n_chunks,
                                                                                                              d->ctx->d_tabs, (uint32_t*)d->k1_first.p);
     frame_scan_kernel<<<(C.n_chunks + 127) / 128, 128, 0, st>>>(C.d_data, (uint32_t)nbytes, C.chunk_bytes, C.n_chunks, v, d->ctx->d_tabs, (const uint32_t*)d->k1_first.p,
-                                                             (ChunkInfo*)d->chunks.p, (uint32_t*)d->chunk_cnt.p, d_fr);
+                                                             (ChunkInfo*)d->chunks.p, (uint32_t*)d->chunk_cnt.p, (uint32_t*)d->k1_stage.p, d_fr);
     frame_check_kernel<<<(C.n_chunks + 255) / 256, 256, 0, st>>>((const ChunkInfo*)d->chunks.p, C.n_chunks, d_fr);
     frame_repair_kernel<<<1, 32, 0, st>>>(C.d_data, (uint32_t)nbytes, C.chunk_bytes, C.n_chunks, v, d->ctx->d_tabs, (ChunkInfo*)d->chunks.p,
-                                          (uint32_t*)d->chunk_cnt.p, d_fr);
+                                          (uint32_t*)d->chunk_cnt.p, (uint32_t*)d->k1_stage.p, d_fr);
     frame_stop_kernel<<<(C.n_chunks + 255) / 256, 256, 0, st>>>((const ChunkInfo*)d->chunks.p, C.n_chunks, d_stop);
     scan_tile_sums_kernel<<<dim3(kt, 1), SCAN_THREADS, 0, st>>>((const uint32_t*)d->chunk_cnt.p, C.n_chunks, kt, tsum);
     scan_tile_bases_kernel<<<1, 1024, 0, st>>>(tsum, kt, traw, d_stop + 1);

@@ -19,6 +19,8 @@
 #pragma once
 #include "common.cuh"
 
+#define FRAME_STAGE 256u      // record offsets staged per chunk by the chain walk (frame_emit copies them; longer chains are re-walked)
+
 // how a chunk's chain (or the whole stream) stopped
 enum {
   FS_LEFT = 0,        // walked past the end of the chunk: `end` is the next record start
@@ -50,7 +52,7 @@ struct FrameResult {       // written by the device, read back by the host (one 
 
 // walk headers starting at q until the chain leaves [.., ce) or stops; returns stop code
 __device__ __forceinline__ uint32_t frame_chain(const uint32_t* t0, const uint8_t* data, uint32_t nbytes, uint32_t ce,
-                                                bool verify, uint32_t& q, uint32_t& count, uint32_t& max_len) {
+                                                bool verify, uint32_t& q, uint32_t& count, uint32_t& max_len, uint32_t* stage = nullptr) {
   while (q < ce) {
     uint32_t left = nbytes - q;
     if (left < 8) return FS_STRAY;
@@ -62,6 +64,7 @@ __device__ __forceinline__ uint32_t frame_chain(const uint32_t* t0, const uint8_
     }
     if (hi != 0 || lo > 0x7fffffffu) return FS_TOO_LARGE;
     if ((uint64_t)left < 16ull + lo) return FS_PART_REC;
+    if (stage && count < FRAME_STAGE) stage[count] = q;
     q += 16 + lo;
     max_len = max(max_len, lo);
     ++count;
@@ -111,7 +114,7 @@ __global__ void __launch_bounds__(256) frame_search_kernel(const uint8_t* __rest
 __global__ void __launch_bounds__(128) frame_scan_kernel(const uint8_t* __restrict__ data, uint32_t nbytes, uint32_t chunk_bytes,
                                                          uint32_t n_chunks, uint32_t verify, const CrcTables* __restrict__ tabs,
                                                          const uint32_t* __restrict__ first_in, ChunkInfo* __restrict__ chunks,
-                                                         uint32_t* __restrict__ chunk_cnt, FrameResult* __restrict__ res) {
+                                                         uint32_t* __restrict__ chunk_cnt, uint32_t* __restrict__ stage, FrameResult* __restrict__ res) {
   __shared__ uint32_t t0[256];
   for (int i = threadIdx.x; i < 256; i += blockDim.x) t0[i] = tabs->t0[i];
   __syncthreads();
@@ -124,7 +127,7 @@ __global__ void __launch_bounds__(128) frame_scan_kernel(const uint8_t* __restri
   ci.first = first; ci.end = first; ci.count = 0; ci.stop = FS_NONE;
   if (first != 0xffffffffu) {
     uint32_t q = first, cnt = 0, mx = 0;
-    ci.stop = frame_chain(t0, data, nbytes, ce, verify != 0, q, cnt, mx);
+    ci.stop = frame_chain(t0, data, nbytes, ce, verify != 0, q, cnt, mx, stage + (size_t)k * FRAME_STAGE);
     ci.end = q; ci.count = cnt;
     if (mx) atomicMax(&res->max_len, mx);                                  // a false candidate can only enlarge the bound
   }
@@ -147,7 +150,7 @@ __global__ void frame_check_kernel(const ChunkInfo* __restrict__ chunks, uint32_
 // Starts at the first broken link and re-chains until the speculation re-synchronises.
 __global__ void frame_repair_kernel(const uint8_t* __restrict__ data, uint32_t nbytes, uint32_t chunk_bytes, uint32_t n_chunks,
                                     uint32_t verify, const CrcTables* __restrict__ tabs, ChunkInfo* __restrict__ chunks,
-                                    uint32_t* __restrict__ chunk_cnt, FrameResult* __restrict__ res) {
+                                    uint32_t* __restrict__ chunk_cnt, uint32_t* __restrict__ stage, FrameResult* __restrict__ res) {
   __shared__ uint32_t t0[256];
   for (int i = threadIdx.x; i < 256; i += blockDim.x) t0[i] = tabs->t0[i];
   __syncthreads();
@@ -175,7 +178,7 @@ __global__ void frame_repair_kernel(const uint8_t* __restrict__ data, uint32_t n
     }
     uint32_t q = F, cnt = 0, mx = 0;
     ci.first = F;
-    ci.stop = frame_chain(t0, data, nbytes, ce, verify != 0, q, cnt, mx);
+    ci.stop = frame_chain(t0, data, nbytes, ce, verify != 0, q, cnt, mx, stage + (size_t)k * FRAME_STAGE);
     if (mx) atomicMax(&res->max_len, mx);
     ci.end = q; ci.count = cnt;
     chunks[k] = ci; chunk_cnt[k] = cnt; ++repairs;
@@ -204,20 +207,29 @@ __global__ void frame_finish_kernel(const ChunkInfo* __restrict__ chunks, uint32
   res->stop = ci.stop; res->stop_pos = ci.end;
 }
 
-// re-walk each chunk (one thread per chunk) and write the record offsets; rec_off[n] = stop_pos
-__global__ void __launch_bounds__(128) frame_emit_kernel(const uint8_t* __restrict__ data, const ChunkInfo* __restrict__ chunks,
-                                                         const uint32_t* __restrict__ chunk_base, uint32_t n_chunks,
+// rec_off[] from the staged offsets: FRAME_EMIT_LANES threads per chunk copy (coalesced), chains longer than the
+// staging capacity are re-walked from the last staged record; rec_off[n] = stop_pos
+#define FRAME_EMIT_LANES 8u
+__global__ void __launch_bounds__(256) frame_emit_kernel(const uint8_t* __restrict__ data, const ChunkInfo* __restrict__ chunks,
+                                                         const uint32_t* __restrict__ chunk_base, uint32_t n_chunks, const uint32_t* __restrict__ stage,
                                                          const FrameResult* __restrict__ res, uint32_t* __restrict__ rec_off) {
   const uint32_t n = res->n_records;
-  const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
-  if (k == 0) rec_off[n] = res->stop_pos;
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t == 0) rec_off[n] = res->stop_pos;
+  const uint32_t k = t / FRAME_EMIT_LANES, sub = t % FRAME_EMIT_LANES;
   if (k >= n_chunks) return;
   ChunkInfo ci = chunks[k];
   if (ci.first == 0xffffffffu || ci.count == 0) return;
   const uint32_t base = chunk_base[k];
-  uint32_t q = ci.first;
-  for (uint32_t i = 0; i < ci.count && base + i < n; ++i) {
-    rec_off[base + i] = q;
+  const uint32_t* st = stage + (size_t)k * FRAME_STAGE;
+  const uint32_t staged = min(ci.count, FRAME_STAGE);
+  for (uint32_t i = sub; i < staged && base + i < n; i += FRAME_EMIT_LANES) rec_off[base + i] = st[i];
+  if (sub == 0 && ci.count > FRAME_STAGE) {
+    uint32_t q = st[FRAME_STAGE - 1];
     q += 16 + load_u32_unaligned(data + q);
+    for (uint32_t i = FRAME_STAGE; i < ci.count && base + i < n; ++i) {
+      rec_off[base + i] = q;
+      q += 16 + load_u32_unaligned(data + q);
+    }
   }
 }
