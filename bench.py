@@ -45,7 +45,7 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=16)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch-mib", type=int, default=512, help="framed bytes per step (approx.)")
+    ap.add_argument("--batch-mib", type=int, default=1024, help="framed bytes per step (approx.)")
     ap.add_argument("--pool", type=int, default=2, help="distinct batches cycled through")
     ap.add_argument("--cpu-sample-mib", type=int, default=48, help="framed bytes each host thread decodes per pass")
     ap.add_argument("--no-e2e", action="store_true")
@@ -185,7 +185,7 @@ def workload_config(args, n_records, batch_bytes, extra=None):
     c = {"workload": "configs[1]: Example decode, 32xInt64List[1] + 16xFloatList[8] + 16xBytesList[1](16 B), CRC verified, -> Arrow columns",
          "records_per_step": n_records, "framed_bytes_per_step": batch_bytes,
          "mean_framed_record_bytes": round(batch_bytes / max(1, n_records), 1),
-         "l2": "each step's input (>= 256 MiB) is larger than the 126 MB L2; batches cycle through a pool",
+         "l2": "each step's input (1 GiB by default) is larger than the 126 MB L2; batches cycle through a pool",
          "pool_batches": args.pool}
     if extra:
         c.update(extra)

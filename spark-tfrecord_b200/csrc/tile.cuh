@@ -102,25 +102,45 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t phase) {
 }
 
 // ---- shared-memory byte helpers (offsets into the tile, not pointers: 32-bit address arithmetic) --
+// The loads are explicit ld.shared on a 32-bit shared-window address held in a register: through a generic pointer the
+// compiler re-derives the window base (S2R SR_CgaCtaId + LEA) at most access sites, ~5% of the kernel's instructions.
+// The tile is read-only after the mbarrier wait; `s` is produced by a volatile asm placed after that wait so that no
+// load can be scheduled above it.
 struct Tile {
-  const uint8_t* b;   // tile base in shared memory (16-byte aligned)
+  const uint8_t* b;   // tile base in shared memory (16-byte aligned), generic pointer for the rare helper calls
+  uint32_t s;         // the same address in the shared window
+  __device__ __forceinline__ uint32_t u8(uint32_t o) const {
+    uint32_t v;
+    asm("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(s + o));
+    return v;
+  }
+  __device__ __forceinline__ int32_t i8(uint32_t o) const {
+    int32_t v;
+    asm("ld.shared.s8 %0, [%1];" : "=r"(v) : "r"(s + o));
+    return v;
+  }
+  __device__ __forceinline__ uint32_t w32(uint32_t o) const {   // aligned word
+    uint32_t v;
+    asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(s + o));
+    return v;
+  }
 };
 __device__ __forceinline__ uint32_t t_u32(const Tile& t, uint32_t o) {   // 4 bytes at any alignment
-  const uint32_t* w = reinterpret_cast<const uint32_t*>(t.b + (o & ~3u));
+  const uint32_t a = o & ~3u;
   uint32_t sh = (o & 3u) * 8;
-  uint32_t lo = w[0];
-  return sh ? __funnelshift_r(lo, w[1], sh) : lo;
+  uint32_t lo = t.w32(a);
+  return sh ? __funnelshift_r(lo, t.w32(a + 4), sh) : lo;
 }
 // length varint: 1..5 bytes (minimal or not); false if it runs past `end` or is longer (-> general path)
 __device__ __forceinline__ bool t_len(const Tile& t, uint32_t& p, uint32_t end, uint32_t& v) {
   if (p >= end) return false;
-  uint32_t b = t.b[p++];
+  uint32_t b = t.u8(p++);
   if (b < 0x80) { v = b; return true; }
   uint32_t r = b & 0x7f;
 #pragma unroll 1
   for (int sh = 7; sh < 35; sh += 7) {
     if (p >= end) return false;
-    b = t.b[p++];
+    b = t.u8(p++);
     r |= (b & 0x7f) << sh;
     if (b < 0x80) { v = r; return (int32_t)r >= 0; }
   }
@@ -247,7 +267,9 @@ __global__ void __launch_bounds__(TILE_THREADS) decode_tile_kernel(TileArgs A) {
   if (active) { off = A.rec_off[row]; len = A.rec_off[row + 1] - off - 16; }
   const uint32_t pay = off - g0 + 12;            // payload offset inside the tile
   const uint32_t end = pay + len;
-  Tile T{tile_b};
+  Tile T;
+  T.b = tile_b;
+  asm volatile("mov.u32 %0, %1;" : "=r"(T.s) : "r"(smem_u32(tile_b)) : "memory");   // ordered after mbar_wait
 
   // =============================== last warp: CRC ===============================
   if (wid == TILE_PARSE_WARPS) {
@@ -269,7 +291,7 @@ __global__ void __launch_bounds__(TILE_THREADS) decode_tile_kernel(TileArgs A) {
     uint32_t p = pay, L = 0;
     uint32_t cend = end, fl_start = end, fl_end = end;      // context/features region = [p, cend), feature_lists = [fl_start, fl_end)
     // Example { features = 1 } / SequenceExample { context = 1, feature_lists = 2 }: exactly these fields, in this order
-    if (len < 2 || T.b[p] != 0x0A) bad = true;
+    if (len < 2 || T.u8(p) != 0x0A) bad = true;
     else {
       ++p;
       if (!t_len(T, p, end, L) || end - p < L) bad = true;
@@ -277,7 +299,7 @@ __global__ void __launch_bounds__(TILE_THREADS) decode_tile_kernel(TileArgs A) {
       else {
         cend = p + L;
         uint32_t q = cend, L2 = 0;
-        if (q >= end || T.b[q] != 0x12) bad = true;
+        if (q >= end || T.u8(q) != 0x12) bad = true;
         else { ++q; if (!t_len(T, q, end, L2) || q + L2 != end) bad = true; else { fl_start = q; fl_end = end; } }
       }
     }
@@ -287,17 +309,23 @@ __global__ void __launch_bounds__(TILE_THREADS) decode_tile_kernel(TileArgs A) {
       // The owner validates those entries; p + 1 <= cend is always inside the tile and an overshoot is caught by the
       // p == cend check after the loop.
       uint32_t skip = (wid - entry_idx) & (TILE_PARSE_WARPS - 1);
-      while (skip && p < cend) {
-        ++entry_idx;
-        const uint32_t b1 = T.b[p + 1];
-        if (b1 < 0x80) p += 2 + b1;
-        else {
+      entry_idx += skip;
+      for (bool wide = true; wide;) {
+        wide = false;
+        while (skip && p < cend) {                           // the tight part: single-byte entry lengths only
+          const int32_t b1 = T.i8(p + 1);
+          if (b1 < 0) { wide = true; break; }
+          p += 2u + (uint32_t)b1;
+          --skip;
+        }
+        if (wide) {                                          // an entry of 128+ bytes: full length varint, then back to the loop
           uint32_t q = p + 1, el;
           if (!t_len(T, q, cend, el)) { bad = true; break; }
           p = q + el;
+          --skip;
         }
-        --skip;
       }
+      entry_idx -= skip;                                     // hops not performed (ran into cend)
       if (bad || p >= cend) break;
       ++entry_idx;                                           // the entry this warp owns
       // ---- owned entry: try the expected field's template first ----
@@ -311,7 +339,7 @@ __global__ void __launch_bounds__(TILE_THREADS) decode_tile_kernel(TileArgs A) {
 #pragma unroll
         for (int w = 0; w < TILE_TPL_WORDS; ++w)
           if ((uint32_t)w < tp.n_words) diff |= (t_u32(T, p + 4 * w) ^ tp.words[w]) & tp.mask[w];
-        const uint32_t elen = T.b[p + 1], vl = T.b[p + 5 + klen], ll = T.b[p + 7 + klen];
+        const uint32_t elen = T.u8(p + 1), vl = T.u8(p + 5 + klen), ll = T.u8(p + 7 + klen);
         // single-byte lengths that nest exactly: entry = key part (klen+2) + 2 + value; value = 2 + list
         if (diff == 0 && elen < 0x80 && elen == klen + 4 + vl && vl == ll + 2 && p + 2 + elen <= cend) {
           f = (int)next_f; eend = p + 2 + elen; vlen = vl; located = true;
@@ -321,20 +349,20 @@ __global__ void __launch_bounds__(TILE_THREADS) decode_tile_kernel(TileArgs A) {
       if (!located) {
         // ---- generic: 0A elen 0A klen key 12 vlen, key looked up by hash ----
         uint32_t elen, klen;
-        if (T.b[p] != 0x0A) { bad = true; break; }
+        if (T.u8(p) != 0x0A) { bad = true; break; }
         ++p;
         if (!t_len(T, p, cend, elen) || cend - p < elen) { bad = true; break; }
         eend = p + elen;
-        if (p >= eend || T.b[p] != 0x0A) { bad = true; break; }
+        if (p >= eend || T.u8(p) != 0x0A) { bad = true; break; }
         ++p;
         if (!t_len(T, p, eend, klen) || eend - p < klen) { bad = true; break; }
         const uint32_t key = p;
         p += klen;
-        if (p >= eend || T.b[p] != 0x12) { bad = true; break; }
+        if (p >= eend || T.u8(p) != 0x12) { bad = true; break; }
         ++p;
         if (!t_len(T, p, eend, vlen) || p + vlen != eend) { bad = true; break; }
         uint32_t hi = 0;
-        for (uint32_t i = 0; i < klen; ++i) hi |= T.b[key + i];
+        for (uint32_t i = 0; i < klen; ++i) hi |= T.u8(key + i);
         if (hi >= 0x80 && !utf8_valid(T.b + key, klen)) { bad = true; break; }   // malformed key: the general path reports it
         uint32_t h = name_hash(T.b + key, klen);
         uint32_t slot = h & (uint32_t)A.sch.ht_mask;
@@ -344,7 +372,7 @@ __global__ void __launch_bounds__(TILE_THREADS) decode_tile_kernel(TileArgs A) {
           if (sfields[cand].hash == h && sfields[cand].name_len == klen) {
             const uint8_t* nm = snames + sfields[cand].name_off;
             uint32_t diff = 0;
-            for (uint32_t i = 0; i < klen; ++i) diff |= T.b[key + i] ^ nm[i];
+            for (uint32_t i = 0; i < klen; ++i) diff |= T.u8(key + i) ^ nm[i];
             if (diff == 0) { f = cand; break; }
           }
           slot = (slot + 1) & (uint32_t)A.sch.ht_mask;
@@ -359,7 +387,7 @@ __global__ void __launch_bounds__(TILE_THREADS) decode_tile_kernel(TileArgs A) {
       }
       // ---- Feature: exactly one oneof member spanning the value ----
       if (vlen == 0) { if (f >= 0) bad = true; p = eend; continue; }              // kind not set: an error if the schema wants it
-      uint32_t kt = T.b[p++], llen;
+      uint32_t kt = T.u8(p++), llen;
       uint32_t kind = kt == 0x0A ? K_BYTES : kt == 0x12 ? K_FLOAT : kt == 0x1A ? K_INT64 : K_NONE;
       if (kind == K_NONE || !t_len(T, p, eend, llen) || p + llen != eend) { bad = true; break; }
       const DevField* fd = f >= 0 ? &sfields[f] : nullptr;
@@ -371,7 +399,7 @@ __global__ void __launch_bounds__(TILE_THREADS) decode_tile_kernel(TileArgs A) {
         const bool is_str = fd && fd->elem_type == TFR_T_STRING;
         while (p < eend) {
           uint32_t bl;
-          if (T.b[p] != 0x0A) { bad = true; break; }
+          if (T.u8(p) != 0x0A) { bad = true; break; }
           ++p;
           const uint32_t lp = p;
           if (!t_len(T, p, eend, bl) || eend - p < bl) { bad = true; break; }
@@ -379,7 +407,7 @@ __global__ void __launch_bounds__(TILE_THREADS) decode_tile_kernel(TileArgs A) {
             // StringType = Java UTF-8 decode/re-encode: identity for well-formed input; malformed input needs the
             // U+FFFD transcode, which only the general path implements
             uint32_t acc = 0;
-            for (uint32_t i = 0; i < bl; ++i) acc |= T.b[p + i];
+            for (uint32_t i = 0; i < bl; ++i) acc |= T.u8(p + i);
             if (acc >= 0x80 && !utf8_valid(T.b + p, bl)) { bad = true; break; }
           }
           if (n == 0) { first_off = lp + g0; first_len = bl; first_data = p; }
@@ -401,7 +429,7 @@ __global__ void __launch_bounds__(TILE_THREADS) decode_tile_kernel(TileArgs A) {
                     v.x = t_u32(T, first_data + i); v.y = t_u32(T, first_data + i + 4); v.z = t_u32(T, first_data + i + 8); v.w = t_u32(T, first_data + i + 12);
                     *reinterpret_cast<uint4*>(dst + i) = v;
                   }
-                } else for (uint32_t i = 0; i < (uint32_t)ul; ++i) dst[i] = T.b[first_data + i];
+                } else for (uint32_t i = 0; i < (uint32_t)ul; ++i) dst[i] = T.u8(first_data + i);
               }
             } else {
               A.cnt[(size_t)fd->cnt_slot * A.n + row] = first_len;
@@ -420,7 +448,7 @@ __global__ void __launch_bounds__(TILE_THREADS) decode_tile_kernel(TileArgs A) {
         // Int64List / FloatList: empty, or one packed field spanning the list
         uint32_t plen = 0, pk = p;
         if (llen != 0) {
-          if (T.b[p] != 0x0A) { bad = true; break; }
+          if (T.u8(p) != 0x0A) { bad = true; break; }
           ++p;
           if (!t_len(T, p, eend, plen) || p + plen != eend) { bad = true; break; }
           pk = p;
@@ -435,12 +463,12 @@ __global__ void __launch_bounds__(TILE_THREADS) decode_tile_kernel(TileArgs A) {
           n = 0;
           uint32_t run = 0;
           if (plen == 1) {                                   // the most common case: one small value
-            v0 = T.b[pk];
+            v0 = T.u8(pk);
             if (v0 & 0x80) { bad = true; break; }
             n = 1;
           } else {
             for (uint32_t i = 0; i < plen; ++i) {
-              uint32_t b = T.b[pk + i];
+              uint32_t b = T.u8(pk + i);
               if (n == 0) v0 |= (uint64_t)(b & 0x7f) << (7 * run);
               if (b & 0x80) { if (++run >= 10) { bad = true; break; } } else { ++n; run = 0; }
             }
@@ -481,7 +509,7 @@ __global__ void __launch_bounds__(TILE_THREADS) decode_tile_kernel(TileArgs A) {
                 uint32_t q = pk;
                 for (uint32_t e = 0; e < n; ++e) {
                   uint64_t v = 0; uint32_t sh = 0;
-                  for (;;) { uint32_t b = T.b[q++]; v |= (uint64_t)(b & 0x7f) << sh; sh += 7; if (b < 0x80) break; }
+                  for (;;) { uint32_t b = T.u8(q++); v |= (uint64_t)(b & 0x7f) << sh; sh += 7; if (b < 0x80) break; }
                   if (fd->elem_type == TFR_T_INT64) reinterpret_cast<int64_t*>(A.var_values[fd->var_slot])[(size_t)row * n + e] = (int64_t)v;
                   else reinterpret_cast<int32_t*>(A.var_values[fd->var_slot])[(size_t)row * n + e] = (int32_t)(uint32_t)v;
                 }
@@ -503,7 +531,7 @@ __global__ void __launch_bounds__(TILE_THREADS) decode_tile_kernel(TileArgs A) {
       uint32_t skip = (wid - entry_idx) & (TILE_PARSE_WARPS - 1);
       while (skip && p < fl_end) {
         ++entry_idx;
-        const uint32_t b1 = T.b[p + 1];
+        const uint32_t b1 = T.u8(p + 1);
         if (b1 < 0x80) p += 2 + b1;
         else {
           uint32_t q = p + 1, el;
@@ -515,21 +543,21 @@ __global__ void __launch_bounds__(TILE_THREADS) decode_tile_kernel(TileArgs A) {
       if (bad || p >= fl_end) break;
       ++entry_idx;                                           // the entry this warp owns
       uint32_t elen, klen, vlen;
-      if (T.b[p] != 0x0A) { bad = true; break; }
+      if (T.u8(p) != 0x0A) { bad = true; break; }
       ++p;
       const uint32_t entry_pos = p;                           // the entry's length varint: what pass 2's FeatureList walker starts from
       if (!t_len(T, p, fl_end, elen) || fl_end - p < elen) { bad = true; break; }
       const uint32_t eend = p + elen;
-      if (p >= eend || T.b[p] != 0x0A) { bad = true; break; }
+      if (p >= eend || T.u8(p) != 0x0A) { bad = true; break; }
       ++p;
       if (!t_len(T, p, eend, klen) || eend - p < klen) { bad = true; break; }
       const uint32_t key = p;
       p += klen;
-      if (p >= eend || T.b[p] != 0x12) { bad = true; break; }
+      if (p >= eend || T.u8(p) != 0x12) { bad = true; break; }
       ++p;
       if (!t_len(T, p, eend, vlen) || p + vlen != eend) { bad = true; break; }
       uint32_t hi = 0;
-      for (uint32_t i = 0; i < klen; ++i) hi |= T.b[key + i];
+      for (uint32_t i = 0; i < klen; ++i) hi |= T.u8(key + i);
       if (hi >= 0x80 && !utf8_valid(T.b + key, klen)) { bad = true; break; }
       int f = -1;
       {
@@ -541,7 +569,7 @@ __global__ void __launch_bounds__(TILE_THREADS) decode_tile_kernel(TileArgs A) {
           if (sfields[cand].hash == h && sfields[cand].name_len == klen) {
             const uint8_t* nm = snames + sfields[cand].name_off;
             uint32_t diff = 0;
-            for (uint32_t i = 0; i < klen; ++i) diff |= T.b[key + i] ^ nm[i];
+            for (uint32_t i = 0; i < klen; ++i) diff |= T.u8(key + i) ^ nm[i];
             if (diff == 0) { f = cand; break; }
           }
           slot = (slot + 1) & (uint32_t)A.sch.ht_mask;
@@ -559,13 +587,13 @@ __global__ void __launch_bounds__(TILE_THREADS) decode_tile_kernel(TileArgs A) {
       uint32_t steps = 0, tot_n = 0, tot_bytes = 0;
       while (p < eend) {                                      // steps
         uint32_t flen;
-        if (T.b[p] != 0x0A) { bad = true; break; }
+        if (T.u8(p) != 0x0A) { bad = true; break; }
         ++p;
         if (!t_len(T, p, eend, flen) || eend - p < flen) { bad = true; break; }
         const uint32_t fend = p + flen;
         ++steps;
         if (flen == 0) { if (fd) bad = true; continue; }     // kind not set: an error if the schema wants the column
-        uint32_t kt = T.b[p++], llen;
+        uint32_t kt = T.u8(p++), llen;
         uint32_t kind = kt == 0x0A ? K_BYTES : kt == 0x12 ? K_FLOAT : kt == 0x1A ? K_INT64 : K_NONE;
         if (kind == K_NONE || !t_len(T, p, fend, llen) || p + llen != fend) { bad = true; break; }
         if (fd && (uint32_t)fd->kind != kind) { bad = true; break; }
@@ -573,12 +601,12 @@ __global__ void __launch_bounds__(TILE_THREADS) decode_tile_kernel(TileArgs A) {
           const bool is_str = fd && fd->elem_type == TFR_T_STRING;
           while (p < fend) {
             uint32_t bl;
-            if (T.b[p] != 0x0A) { bad = true; break; }
+            if (T.u8(p) != 0x0A) { bad = true; break; }
             ++p;
             if (!t_len(T, p, fend, bl) || fend - p < bl) { bad = true; break; }
             if (is_str) {
               uint32_t acc = 0;
-              for (uint32_t i = 0; i < bl; ++i) acc |= T.b[p + i];
+              for (uint32_t i = 0; i < bl; ++i) acc |= T.u8(p + i);
               if (acc >= 0x80 && !utf8_valid(T.b + p, bl)) { bad = true; break; }
             }
             ++tot_n; tot_bytes += bl;
@@ -587,7 +615,7 @@ __global__ void __launch_bounds__(TILE_THREADS) decode_tile_kernel(TileArgs A) {
           if (bad) break;
         } else if (llen != 0) {
           uint32_t plen;
-          if (T.b[p] != 0x0A) { bad = true; break; }
+          if (T.u8(p) != 0x0A) { bad = true; break; }
           ++p;
           if (!t_len(T, p, fend, plen) || p + plen != fend) { bad = true; break; }
           if (kind == K_FLOAT) {
@@ -596,7 +624,7 @@ __global__ void __launch_bounds__(TILE_THREADS) decode_tile_kernel(TileArgs A) {
           } else {
             uint32_t run = 0;
             for (uint32_t i = 0; i < plen; ++i) {
-              if (T.b[p + i] & 0x80) { if (++run >= 10) { bad = true; break; } } else { ++tot_n; run = 0; }
+              if (T.u8(p + i) & 0x80) { if (++run >= 10) { bad = true; break; } } else { ++tot_n; run = 0; }
             }
             if (bad || run) { bad = true; break; }
           }
