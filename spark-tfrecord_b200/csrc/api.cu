@@ -231,6 +231,7 @@ extern "C" int32_t tfr_schema_num_fields(const tfr_schema* s) { return s ? (int3
 struct DevSchemaBuf {
   DevField* d_fields = nullptr; uint8_t* d_names = nullptr; int32_t* d_ht = nullptr; int32_t* d_var_field = nullptr;
   FieldTemplate* d_templates = nullptr;
+  uint8_t* d_tile_consts = nullptr; uint32_t tile_consts_bytes = 0;     // tile.cuh: per-schema constants in the shared-memory layout
   DevSchema view{};
   int32_t upload(const tfr_schema& s) {
     size_t nf = s.fields.size();
@@ -269,7 +270,23 @@ struct DevSchemaBuf {
     view.fields = d_fields; view.names = d_names; view.ht = d_ht;
     return TFR_OK;
   }
-  void free_all() { cudaFree(d_fields); cudaFree(d_names); cudaFree(d_ht); cudaFree(d_var_field); cudaFree(d_templates); }
+  // CRC tables | zeroed seen words | DevField[nf] | FieldTemplate[nf] | names, each section 16-byte aligned (tile_const_bytes)
+  int32_t build_tile_consts(const tfr_schema& s, const CrcTables* d_tabs) {
+    const uint32_t nf = (uint32_t)s.fields.size(), nb = (uint32_t)s.names.size();
+    tile_consts_bytes = tile_const_bytes(nf, nb);
+    CUDA_TRY(cudaMalloc(&d_tile_consts, tile_consts_bytes));
+    CUDA_TRY(cudaMemset(d_tile_consts, 0, tile_consts_bytes));
+    uint8_t* q = d_tile_consts;
+    CUDA_TRY(cudaMemcpy(q, d_tabs->s8, 8192 + 512, cudaMemcpyDeviceToDevice));      // s8 then xp512, contiguous in CrcTables
+    q += 8192 + 512 + TILE_SEEN_BYTES;
+    if (nf) CUDA_TRY(cudaMemcpy(q, d_fields, nf * sizeof(DevField), cudaMemcpyDeviceToDevice));
+    q += (nf * sizeof(DevField) + 15) & ~(size_t)15;
+    if (nf) CUDA_TRY(cudaMemcpy(q, d_templates, nf * sizeof(FieldTemplate), cudaMemcpyDeviceToDevice));
+    q += (nf * sizeof(FieldTemplate) + 15) & ~(size_t)15;
+    if (nb) CUDA_TRY(cudaMemcpy(q, d_names, nb, cudaMemcpyDeviceToDevice));
+    return TFR_OK;
+  }
+  void free_all() { cudaFree(d_fields); cudaFree(d_names); cudaFree(d_ht); cudaFree(d_var_field); cudaFree(d_templates); cudaFree(d_tile_consts); }
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -361,6 +378,7 @@ extern "C" int32_t tfr_decoder_create(const tfr_schema* schema, int32_t device, 
   d->schema = *schema; d->device = device; d->flags = flags; d->ctx = ctx;
   CUDA_TRY(cudaStreamCreateWithFlags(&d->stream, cudaStreamNonBlocking));
   rc = d->dsch.upload(d->schema);
+  if (!rc) rc = d->dsch.build_tile_consts(d->schema, ctx->d_tabs);
   if (rc) { delete d; return rc; }
   TRY(d->small.ensure(4096 + (size_t)d->schema.n_cnt * 16));
   {
@@ -760,7 +778,11 @@ static int32_t decode_impl(tfr_decoder* d, const void* data, size_t nbytes, int3
     bool done = false;
     // ================= fast path: shared-memory tiles, one record per thread =================
     const uint32_t names_bytes = (uint32_t)S.names.size();
-    const uint32_t tile_cap = (uint32_t)align_up((size_t)TILE_ROWS * ((size_t)fr.max_len + 16) + 32, 128);
+    // one slot per record: 16-byte alignment slack + framed record + over-read slack, an odd number of 16-byte units
+    size_t slot64 = align_up((size_t)fr.max_len + 16 + 15 + 32, 16);
+    if (((slot64 >> 4) & 1) == 0) slot64 += 16;
+    const uint32_t tile_slot = (uint32_t)std::min<size_t>(slot64, 1u << 20);
+    const uint32_t tile_cap = TILE_ROWS * tile_slot;
     const size_t tile_smem = tile_smem_bytes(nf, names_bytes, tile_cap);
     if (try_fast && tile_smem <= (size_t)d->ctx->max_smem_optin) {
       const bool uniform = d->spec_state == 1;
@@ -791,8 +813,8 @@ static int32_t decode_impl(tfr_decoder* d, const void* data, size_t nbytes, int3
       CUDA_TRY(cudaMemcpyAsync(d->uniform_dev.p, d->h_uniform, (size_t)std::max(1, S.n_var) * 4, cudaMemcpyHostToDevice, st));
       CUDA_TRY(cudaMemsetAsync(dflags_ptr(d), 0, 4, st));
       TileArgs TA{};
-      TA.data = C.d_data; TA.nbytes = (uint32_t)nbytes; TA.rec_off = (const uint32_t*)d->rec_off.p; TA.n = n; TA.tile_cap = tile_cap;
-      TA.verify = C.verify; TA.names_bytes = names_bytes; TA.sch = d->dsch.view; TA.templates = d->dsch.d_templates; TA.tabs = d->ctx->d_tabs;
+      TA.data = C.d_data; TA.nbytes = (uint32_t)nbytes; TA.rec_off = (const uint32_t*)d->rec_off.p; TA.n = n; TA.tile_cap = tile_cap; TA.slot = tile_slot;
+      TA.verify = C.verify; TA.names_bytes = names_bytes; TA.sch = d->dsch.view; TA.consts = d->dsch.d_tile_consts; TA.const_bytes = d->dsch.tile_consts_bytes;
       TA.bitmaps = C.fx + C.bitmaps_off; TA.nb_stride = C.nb_stride; TA.null_counts = b->d_null_counts;
       TA.fix_values = A.fix_values; TA.cnt = A.cnt; TA.src = A.src; TA.cflag = A.cflag;
       TA.uniform_len = (const int32_t*)d->uniform_dev.p; TA.var_values = (void* const*)C.dt_vals; TA.flags = dflags_ptr(d);

@@ -35,9 +35,12 @@
 
 #define TILE_ROWS 32
 #ifndef TILE_PARSE_WARPS
-#define TILE_PARSE_WARPS 8     // power of two
+#define TILE_PARSE_WARPS 8
 #endif
 #define TILE_THREADS ((TILE_PARSE_WARPS + 1) * 32)
+#ifndef TILE_MIN_CTAS
+#define TILE_MIN_CTAS 3       // registers are capped so that shared memory, not the register file, limits residency
+#endif
 #define TILE_TPL_WORDS 5          // template covers up to 20 bytes: key names up to 12 bytes
 
 // constant bytes of a canonical map entry of one schema field, for masked word compares
@@ -53,12 +56,13 @@ struct TileArgs {
   uint32_t nbytes;
   const uint32_t* rec_off;      // [n+1]
   uint32_t n;                   // rows in the batch (stride of the scratch arrays)
-  uint32_t tile_cap;            // bytes of shared memory reserved for the record bytes of one tile
+  uint32_t tile_cap;            // bytes of shared memory reserved for the record bytes of one tile (TILE_ROWS slots)
+  uint32_t slot;                // bytes per record slot: an ODD multiple of 16 (bank-group spread, see crc_tile)
   uint32_t verify;
   uint32_t names_bytes;
   DevSchema sch;
-  const FieldTemplate* templates;   // [n_fields]
-  const CrcTables* tabs;
+  const uint8_t* consts;        // per-schema constants in the shared-memory layout (CRC tables | seen zeros | fields | templates | names)
+  uint32_t const_bytes;         // multiple of 16
   uint8_t* bitmaps;             // [nf][nb_stride] Arrow validity bitmaps, written directly
   uint32_t nb_stride;
   unsigned long long* null_counts;   // [nf]
@@ -119,6 +123,11 @@ struct Tile {
     asm("ld.shared.s8 %0, [%1];" : "=r"(v) : "r"(s + o));
     return v;
   }
+  __device__ __forceinline__ uint4 w128(uint32_t o) const {     // 16-byte aligned
+    uint4 v;
+    asm("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(s + o));
+    return v;
+  }
   __device__ __forceinline__ uint32_t w32(uint32_t o) const {   // aligned word
     uint32_t v;
     asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(s + o));
@@ -154,67 +163,73 @@ __device__ __forceinline__ uint32_t crc_fold8(const uint32_t* s8, uint32_t c, ui
   return s8[7 * 256 + (a & 0xff)] ^ s8[6 * 256 + ((a >> 8) & 0xff)] ^ s8[5 * 256 + ((a >> 16) & 0xff)] ^ s8[4 * 256 + (a >> 24)] ^
          s8[3 * 256 + (hi & 0xff)] ^ s8[2 * 256 + ((hi >> 8) & 0xff)] ^ s8[1 * 256 + ((hi >> 16) & 0xff)] ^ s8[(hi >> 24)];
 }
-// serial: state `c` over n bytes at tile offset o (any alignment)
-__device__ __forceinline__ uint32_t crc_serial_s8(const uint32_t* s8, const uint8_t* base, uint32_t o, uint32_t n, uint32_t c) {
-  while (n && (o & 3)) { c = (c >> 8) ^ s8[(c ^ base[o++]) & 0xff]; --n; }
-  const uint32_t* w = reinterpret_cast<const uint32_t*>(base + o);
-  uint32_t nw = n >> 3;
+// CRC-32C of n bytes at tile offset o, one record per thread.
+//  * bytes up to the first 16-byte boundary go through the byte-wise table, everything after is read with aligned
+//    128-bit loads: the records of a tile sit in slots whose stride is an odd multiple of 16 bytes, so the 32 lanes
+//    of a warp spread over all eight 16-byte bank groups and a 128-bit load costs the minimum of 4 wavefronts
+//    (with 32-bit loads at a record stride of 1728 B every data load was a 16-way bank conflict).
+//  * a serial CRC is one long dependent chain (a table round trip per 8 bytes): the aligned body is cut into 512-byte
+//    segments, three segment chains run interleaved in the same thread, each segment state is shifted over the
+//    segments that follow it with ONE GF(2) multiply by the constant x^(8*512*m) (xp512), and the < 512-byte tail is
+//    folded serially from the combined state.  CRC(A||B) = CRC_B(0) ^ shift_|B|(CRC_A).
+#define CRC_SEG 512u
+__device__ __forceinline__ uint32_t crc_seg1(const uint32_t* s8, const Tile& t, uint32_t o, uint32_t c) {   // one 512-byte segment
 #pragma unroll 2
-  for (uint32_t i = 0; i < nw; ++i) c = crc_fold8(s8, c, w[2 * i], w[2 * i + 1]);
-  o += nw * 8; n &= 7;
-  while (n--) c = (c >> 8) ^ s8[(c ^ base[o++]) & 0xff];
+  for (uint32_t i = 0; i < CRC_SEG / 16; ++i) {
+    const uint4 v = t.w128(o + 16 * i);
+    c = crc_fold8(s8, c, v.x, v.y);
+    c = crc_fold8(s8, c, v.z, v.w);
+  }
   return c;
 }
-// A serial CRC is one long dependent chain (one table-lookup round trip per 8 bytes).  The payload is cut
-// into 512-byte segments; three segment chains run interleaved in the same thread (independent
-// registers -> the LDS latencies overlap), each segment state is shifted over the segments that follow
-// it with ONE GF(2) multiply by the table constant x^(8*512*m) (xp512, in shared memory) and the
-// < 512-byte tail is folded serially from the combined state.  CRC(A||B) = CRC_B(0) ^ shift_|B|(CRC_A).
-#define CRC_SEG 512u
-__device__ __forceinline__ uint32_t crc_segmented(const uint32_t* s8, const uint32_t* xp, const uint8_t* base, uint32_t o, uint32_t n) {
-  const uint32_t nF = n / CRC_SEG;
-  if (nF == 0 || nF > 127) return ~crc_serial_s8(s8, base, o, n, 0xFFFFFFFFu);
-  const uint32_t sh = (o & 3u) * 8;
-  const uint32_t* W = reinterpret_cast<const uint32_t*>(base + (o & ~3u));     // aligned words; chain k starts at W + k*128
-  uint32_t acc = 0, j = 0;
-  for (; j + 3 <= nF; j += 3) {
-    const uint32_t* w0 = W + j * (CRC_SEG / 4);
-    const uint32_t* w1 = w0 + CRC_SEG / 4;
-    const uint32_t* w2 = w1 + CRC_SEG / 4;
-    uint32_t c0 = j == 0 ? 0xFFFFFFFFu : 0u, c1 = 0, c2 = 0;
-    uint32_t k0 = w0[0], k1 = w1[0], k2 = w2[0];                               // carry words for the funnel shifts
-#pragma unroll 4
-    for (uint32_t i = 0; i < CRC_SEG / 8; ++i) {
-      uint32_t a0 = w0[2 * i + 1], b0 = w0[2 * i + 2], a1 = w1[2 * i + 1], b1 = w1[2 * i + 2], a2 = w2[2 * i + 1], b2 = w2[2 * i + 2];
-      c0 = crc_fold8(s8, c0, __funnelshift_r(k0, a0, sh), __funnelshift_r(a0, b0, sh)); k0 = b0;
-      c1 = crc_fold8(s8, c1, __funnelshift_r(k1, a1, sh), __funnelshift_r(a1, b1, sh)); k1 = b1;
-      c2 = crc_fold8(s8, c2, __funnelshift_r(k2, a2, sh), __funnelshift_r(a2, b2, sh)); k2 = b2;
+__device__ __forceinline__ uint32_t crc_tile(const uint32_t* s8, const uint32_t* xp, const Tile& t, uint32_t o, uint32_t n) {
+  uint32_t c = 0xFFFFFFFFu;
+  while (n && (o & 15u)) { c = (c >> 8) ^ s8[(c ^ t.u8(o++)) & 0xff]; --n; }
+  const uint32_t nF = n / CRC_SEG;                                  // < 16: a record fits a slot of the tile
+  if (nF) {
+    uint32_t acc = 0, j = 0;
+    for (; j + 3 <= nF; j += 3) {
+      const uint32_t a = o + j * CRC_SEG;
+      uint32_t c0 = j == 0 ? c : 0u, c1 = 0, c2 = 0;
+#pragma unroll 2
+      for (uint32_t i = 0; i < CRC_SEG / 16; ++i) {
+        const uint4 v0 = t.w128(a + 16 * i), v1 = t.w128(a + CRC_SEG + 16 * i), v2 = t.w128(a + 2 * CRC_SEG + 16 * i);
+        c0 = crc_fold8(s8, c0, v0.x, v0.y); c1 = crc_fold8(s8, c1, v1.x, v1.y); c2 = crc_fold8(s8, c2, v2.x, v2.y);
+        c0 = crc_fold8(s8, c0, v0.z, v0.w); c1 = crc_fold8(s8, c1, v1.z, v1.w); c2 = crc_fold8(s8, c2, v2.z, v2.w);
+      }
+      acc ^= gf2_mulmod(xp[nF - 1 - j], c0) ^ gf2_mulmod(xp[nF - 2 - j], c1) ^ gf2_mulmod(xp[nF - 3 - j], c2);
     }
-    acc ^= gf2_mulmod(xp[nF - 1 - j], c0) ^ gf2_mulmod(xp[nF - 2 - j], c1) ^ gf2_mulmod(xp[nF - 3 - j], c2);
+    for (; j < nF; ++j) acc ^= gf2_mulmod(xp[nF - 1 - j], crc_seg1(s8, t, o + j * CRC_SEG, j == 0 ? c : 0u));
+    c = acc; o += nF * CRC_SEG; n -= nF * CRC_SEG;
   }
-  for (; j < nF; ++j) {
-    uint32_t c = crc_serial_s8(s8, base, o + j * CRC_SEG, CRC_SEG, j == 0 ? 0xFFFFFFFFu : 0u);
-    acc ^= gf2_mulmod(xp[nF - 1 - j], c);
+  for (; n >= 16; n -= 16, o += 16) {
+    const uint4 v = t.w128(o);
+    c = crc_fold8(s8, c, v.x, v.y);
+    c = crc_fold8(s8, c, v.z, v.w);
   }
-  return ~crc_serial_s8(s8, base, o + nF * CRC_SEG, n - nF * CRC_SEG, acc);
+  while (n--) c = (c >> 8) ^ s8[(c ^ t.u8(o++)) & 0xff];
+  return ~c;
 }
 
 // shared memory layout (dynamic), all sections 16-byte aligned:
-//   [0,16) mbarrier | CRC tables 8 KiB + xp512 512 B | seen masks [W][32][2] u64 | DevField[nf] | FieldTemplate[nf] | names | tile bytes
-#define TILE_SEEN_BYTES (TILE_PARSE_WARPS * 32 * 16)
+//   [0,16) mbarrier | CRC tables 8 KiB + xp512 512 B | seen words [32][4] u32 | DevField[nf] | FieldTemplate[nf] | names | tile bytes
+// Everything between the mbarrier and the tile is constant per schema ("consts": built once per decoder in this layout,
+// api.cu) and arrives with ONE bulk copy on the same mbarrier as the tile.
+#define TILE_SEEN_BYTES 512u
 __host__ __device__ inline uint32_t tile_schema_smem(uint32_t nf, uint32_t names_bytes) {
   return ((nf * (uint32_t)sizeof(DevField) + 15u) & ~15u) + ((nf * (uint32_t)sizeof(FieldTemplate) + 15u) & ~15u) + ((names_bytes + 15u) & ~15u);
 }
+__host__ __device__ inline uint32_t tile_const_bytes(uint32_t nf, uint32_t names_bytes) { return 8192 + 512 + TILE_SEEN_BYTES + tile_schema_smem(nf, names_bytes); }
 __host__ __device__ inline uint32_t tile_smem_bytes(uint32_t nf, uint32_t names_bytes, uint32_t tile_cap) {
-  return 16 + 8192 + 512 + TILE_SEEN_BYTES + tile_schema_smem(nf, names_bytes) + tile_cap + 64;   // +64: template compares may look a few bytes past the tile
+  return 16 + tile_const_bytes(nf, names_bytes) + tile_cap + 64;   // +64: template compares may look a few bytes past the tile
 }
 
 template <bool SEQ>
-__global__ void __launch_bounds__(TILE_THREADS) decode_tile_kernel(TileArgs A) {
+__global__ void __launch_bounds__(TILE_THREADS, TILE_MIN_CTAS) decode_tile_kernel(TileArgs A) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
   uint32_t* s8 = reinterpret_cast<uint32_t*>(smem_raw + 16);                               // 8 KiB
-  unsigned long long* sseen = reinterpret_cast<unsigned long long*>(smem_raw + 16 + 8192 + 512);
+  uint32_t* sseen = reinterpret_cast<uint32_t*>(smem_raw + 16 + 8192 + 512);                 // [32 rows][4 words], zero in the consts blob
   const uint32_t nf = (uint32_t)A.sch.n_fields;
   uint8_t* sbase = smem_raw + 16 + 8192 + 512 + TILE_SEEN_BYTES;
   DevField* sfields = reinterpret_cast<DevField*>(sbase);
@@ -223,50 +238,51 @@ __global__ void __launch_bounds__(TILE_THREADS) decode_tile_kernel(TileArgs A) {
   uint8_t* tile_b = sbase + tile_schema_smem(nf, A.names_bytes);
   const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;                          // warps 0..W-1 parse, warp W = CRC
 
+  // Record r of the tile is copied into its own slot: bytes [off_r & ~15, off_r + framed length) -> tile + r * slot.
+  // (cp.async.bulk wants 16-byte aligned source, destination and size; the record starts (off_r & 15) bytes into its slot.)
   const uint32_t row0 = blockIdx.x * TILE_ROWS;
   const uint32_t rows = min((uint32_t)TILE_ROWS, A.n - row0);
-  const uint32_t first = A.rec_off[row0], last = A.rec_off[row0 + rows];
-  const uint32_t g0 = first & ~15u;
-  const uint32_t span = last - g0;
-  if (span > A.tile_cap) {                                        // records too large for the tile: general path
+  const bool active = lane < rows;
+  const uint32_t row = row0 + lane;
+  uint32_t off = 0, flen = 16;
+  if (active) { off = A.rec_off[row]; flen = A.rec_off[row + 1] - off; }
+  const uint32_t head = off & 15u;
+  const uint32_t cbytes = active ? (head + flen + 15u) & ~15u : 0u;       // may read < 16 bytes past the end (input buffers are padded)
+  if (__any_sync(FULLMASK, cbytes + 32u > A.slot)) {                       // a record too large for its slot: general path
     if (threadIdx.x == 0) atomicOr(A.flags, TF_FALLBACK);
     return;
   }
-  const uint32_t copy_bytes = (span + 15u) & ~15u;                // may read < 16 bytes past the end (input buffers are padded)
-  if (threadIdx.x == 0) {
-    mbar_init(bar, 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    mbar_expect_tx(bar, copy_bytes);
-    uint32_t done = 0;
-    while (done < copy_bytes) {
-      uint32_t part = min(copy_bytes - done, 32768u);
-      bulk_g2s(tile_b + done, A.data + g0 + done, part, bar);
-      done += part;
+  if (wid == 0) {
+    if (lane == 0) {
+      mbar_init(bar, 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    const uint32_t total = __reduce_add_sync(FULLMASK, cbytes);
+    if (lane == 0) {
+#if defined(TILE_CONSTS_LDG)
+      mbar_expect_tx(bar, total);
+#else
+      mbar_expect_tx(bar, total + A.const_bytes);
+      bulk_g2s(smem_raw + 16, A.consts, A.const_bytes, bar);      // CRC tables, zeroed seen words, schema, templates, names
+#endif
+    }
+    __syncwarp();
+    if (cbytes) bulk_g2s(tile_b + lane * A.slot, A.data + (off - head), cbytes, bar);
   }
-  {   // meanwhile: CRC tables + schema into shared memory
-    const uint32_t* g = reinterpret_cast<const uint32_t*>(A.tabs->s8);
-    for (uint32_t i = threadIdx.x; i < 2048 + 128; i += TILE_THREADS) s8[i] = g[i];      // s8 tables, then xp512 (contiguous in CrcTables)
-    const uint32_t* gf = reinterpret_cast<const uint32_t*>(A.sch.fields);
-    uint32_t* sf = reinterpret_cast<uint32_t*>(sfields);
-    for (uint32_t i = threadIdx.x; i < nf * (uint32_t)(sizeof(DevField) / 4); i += TILE_THREADS) sf[i] = gf[i];
-    const uint32_t* gt = reinterpret_cast<const uint32_t*>(A.templates);
-    uint32_t* stw = reinterpret_cast<uint32_t*>(stpl);
-    for (uint32_t i = threadIdx.x; i < nf * (uint32_t)(sizeof(FieldTemplate) / 4); i += TILE_THREADS) stw[i] = gt[i];
-    for (uint32_t i = threadIdx.x; i < A.names_bytes; i += TILE_THREADS) snames[i] = A.sch.names[i];
+#if defined(TILE_CONSTS_LDG)
+  {
+    const uint4* g = reinterpret_cast<const uint4*>(A.consts);
+    uint4* sd = reinterpret_cast<uint4*>(smem_raw + 16);
+    for (uint32_t i = threadIdx.x; i < A.const_bytes / 16; i += TILE_THREADS) sd[i] = __ldg(g + i);
   }
-  __syncthreads();
+#endif
+  __syncthreads();                                                // the barrier is initialised before anyone waits on it
   mbar_wait(bar, 0);
 
-  const bool active = lane < rows;
-  const uint32_t row = row0 + lane;
-  uint32_t off = 0, len = 0;
-  if (active) { off = A.rec_off[row]; len = A.rec_off[row + 1] - off - 16; }
-  const uint32_t pay = off - g0 + 12;            // payload offset inside the tile
+  const uint32_t len = flen - 16;
+  const uint32_t pay = lane * A.slot + head + 12;                 // payload offset inside the tile
   const uint32_t end = pay + len;
+  const uint32_t g0 = (off - head) - lane * A.slot;               // tile offset + g0 = offset in the batch (mod 2^32)
   Tile T;
   T.b = tile_b;
   asm volatile("mov.u32 %0, %1;" : "=r"(T.s) : "r"(smem_u32(tile_b)) : "memory");   // ordered after mbar_wait
@@ -276,7 +292,7 @@ __global__ void __launch_bounds__(TILE_THREADS) decode_tile_kernel(TileArgs A) {
     if (active && A.verify) {
       // the frame index chained the headers without checking them on the fast path: check the length CRC here
       if (crc_mask(crc_u64(s8, t_u32(T, pay - 12), t_u32(T, pay - 8))) != t_u32(T, pay - 4)) atomicOr(A.flags, TF_FALLBACK);
-      uint32_t crc = crc_segmented(s8, s8 + 2048, tile_b, pay, len);
+      uint32_t crc = crc_tile(s8, s8 + 2048, T, pay, len);
       if (crc_mask(crc) != t_u32(T, end)) atomicOr(A.flags, TF_FALLBACK);      // the general path reports the error at the right record
     }
     return;
@@ -308,7 +324,8 @@ __global__ void __launch_bounds__(TILE_THREADS) decode_tile_kernel(TileArgs A) {
       // hop over the entries the other parse warps own (`0A elen ...`): a tight loop, one byte load + add per entry.
       // The owner validates those entries; p + 1 <= cend is always inside the tile and an overshoot is caught by the
       // p == cend check after the loop.
-      uint32_t skip = (wid - entry_idx) & (TILE_PARSE_WARPS - 1);
+      const uint32_t er = entry_idx % TILE_PARSE_WARPS;
+      uint32_t skip = wid >= er ? wid - er : wid + TILE_PARSE_WARPS - er;
       entry_idx += skip;
       for (bool wide = true; wide;) {
         wide = false;
@@ -528,7 +545,8 @@ __global__ void __launch_bounds__(TILE_THREADS) decode_tile_kernel(TileArgs A) {
     // ---- SequenceExample.feature_lists: { 0A elen 0A klen key 12 vlen FeatureList }*, FeatureList = { 0A flen Feature }* ----
     p = fl_start;
     while (SEQ && !bad && p < fl_end) {
-      uint32_t skip = (wid - entry_idx) & (TILE_PARSE_WARPS - 1);
+      const uint32_t er = entry_idx % TILE_PARSE_WARPS;
+      uint32_t skip = wid >= er ? wid - er : wid + TILE_PARSE_WARPS - er;
       while (skip && p < fl_end) {
         ++entry_idx;
         const uint32_t b1 = T.u8(p + 1);
@@ -643,46 +661,39 @@ __global__ void __launch_bounds__(TILE_THREADS) decode_tile_kernel(TileArgs A) {
     }
     if (!bad && p != fl_end) bad = true;
   }
-  // ---- merge the parse warps' seen masks (a key seen by two warps is a duplicate) ----
-  sseen[(wid * 32 + lane) * 2] = seen_lo;
-  sseen[(wid * 32 + lane) * 2 + 1] = seen_hi;
-  asm volatile("bar.sync 1, %0;" ::"r"(TILE_PARSE_WARPS * 32) : "memory");
-  if (wid == 0) {
-    unsigned long long all_lo = 0, all_hi = 0;
+  // ---- merge the parse warps' seen masks (a key seen by two warps is a duplicate: last-wins -> general path) ----
+  {
+    const uint32_t w4[4] = {(uint32_t)seen_lo, (uint32_t)(seen_lo >> 32), (uint32_t)seen_hi, (uint32_t)(seen_hi >> 32)};
 #pragma unroll
-    for (int w = 0; w < TILE_PARSE_WARPS; ++w) {
-      unsigned long long a = sseen[(w * 32 + lane) * 2], b = sseen[(w * 32 + lane) * 2 + 1];
-      if ((all_lo & a) | (all_hi & b)) bad = true;                            // duplicate key across warps: last-wins -> general path
-      all_lo |= a; all_hi |= b;
-    }
-    seen_lo = all_lo; seen_hi = all_hi;
-    // ---- validity bitmaps by ballot (rows are 32-aligned), absent fields -> null / error ----
+    for (int k = 0; k < 4; ++k)
+      if (w4[k] && (atomicOr(&sseen[lane * 4 + k], w4[k]) & w4[k])) bad = true;
+  }
+  asm volatile("bar.sync 1, %0;" ::"r"(TILE_PARSE_WARPS * 32) : "memory");
+  {
+    // ---- validity bitmaps by ballot (rows are 32-aligned), absent fields -> null / error; field f is finished by warp f % W ----
+    uint32_t all[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) all[k] = sseen[lane * 4 + k];
     const uint32_t act_mask = __ballot_sync(FULLMASK, active);
-    for (uint32_t f0 = 0; f0 < nf; f0 += 32) {
-      uint32_t my_word = 0;
-      const uint32_t lim = min(32u, nf - f0);
-      for (uint32_t j = 0; j < lim; ++j) {
-        const uint32_t f = f0 + j;
-        const bool present = f < 64 ? (seen_lo >> f) & 1 : (seen_hi >> (f - 64)) & 1;
-        const uint32_t m = __ballot_sync(FULLMASK, present && active);
-        if (lane == j) my_word = m;
-        if (active && !present && sfields[f].elem_type != TFR_T_NULL) {
-          const DevField& fd = sfields[f];
-          if (!fd.nullable) bad = true;                                       // NullPointerException: error path
-          if (fd.fix_slot >= 0) {
-            void* vp = A.fix_values[fd.fix_slot];
-            if (fd.width == 8) reinterpret_cast<uint64_t*>(vp)[row] = 0; else reinterpret_cast<uint32_t*>(vp)[row] = 0;
-          } else if (fd.var_slot >= 0) {
-            const int32_t ul = A.uniform_len[fd.var_slot];
-            if (ul > 0) shape_bad = 1;                                        // a null row has no values: not uniform
-            else if (ul < 0) for (int l = 0; l < fd.n_levels; ++l) A.cnt[(size_t)(fd.cnt_slot + l) * A.n + row] = 0;
-          }
+    for (uint32_t f = wid; f < nf; f += TILE_PARSE_WARPS) {
+      const uint32_t wsel = f < 32 ? all[0] : f < 64 ? all[1] : f < 96 ? all[2] : all[3];
+      const bool present = (wsel >> (f & 31)) & 1;
+      const uint32_t m = __ballot_sync(FULLMASK, present && active);
+      if (active && !present && sfields[f].elem_type != TFR_T_NULL) {
+        const DevField& fd = sfields[f];
+        if (!fd.nullable) bad = true;                                         // NullPointerException: error path
+        if (fd.fix_slot >= 0) {
+          void* vp = A.fix_values[fd.fix_slot];
+          if (fd.width == 8) reinterpret_cast<uint64_t*>(vp)[row] = 0; else reinterpret_cast<uint32_t*>(vp)[row] = 0;
+        } else if (fd.var_slot >= 0) {
+          const int32_t ul = A.uniform_len[fd.var_slot];
+          if (ul > 0) shape_bad = 1;                                          // a null row has no values: not uniform
+          else if (ul < 0) for (int l = 0; l < fd.n_levels; ++l) A.cnt[(size_t)(fd.cnt_slot + l) * A.n + row] = 0;
         }
       }
-      if (lane < lim) {
-        const uint32_t f = f0 + lane;
-        reinterpret_cast<uint32_t*>(A.bitmaps + (size_t)f * A.nb_stride)[blockIdx.x] = my_word;
-        const uint32_t nulls = __popc(act_mask & ~my_word);
+      if (lane == 0) {
+        reinterpret_cast<uint32_t*>(A.bitmaps + (size_t)f * A.nb_stride)[blockIdx.x] = m;
+        const uint32_t nulls = __popc(act_mask & ~m);
         if (nulls) atomicAdd(&A.null_counts[f], (unsigned long long)nulls);
       }
     }
