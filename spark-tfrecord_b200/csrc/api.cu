@@ -106,7 +106,19 @@ static void build_crc_tables(CrcTables& t) {
     t.s8[0][i] = t.t0[i];
     for (int k = 1; k < 8; ++k) t.s8[k][i] = (t.s8[k - 1][i] >> 8) ^ t.t0[t.s8[k - 1][i] & 0xff];
   }
-  for (uint32_t m = 0; m < 128; ++m) t.xp512[m] = xpow_bytes(512 * m);
+  for (uint32_t m = 0; m < 512; ++m) t.xp16[m] = xpow_bytes(16 * m);
+  memset(t.g5, 0, sizeof t.g5);
+  for (uint32_t k = 0; k < 13; ++k)
+    for (uint32_t v = 0; v < 32; ++v) {
+      uint32_t r = 0;
+      for (uint32_t j = 0; j < 5; ++j) {
+        const uint32_t bit = 5 * k + j;
+        if (((v >> j) & 1u) && bit < 64) r ^= t.s8[7 - bit / 8][1u << (bit % 8)];
+      }
+      t.g5[k * 32 + v] = r;
+    }
+  for (uint32_t v = 0; v < 32; ++v) t.g5[416 + v] = t.t0[v];
+  for (uint32_t w = 0; w < 8; ++w) t.g5[448 + w] = t.t0[w << 5];
 }
 
 static int32_t get_ctx(int device, DeviceCtx** out) {
@@ -259,7 +271,7 @@ struct DevSchemaBuf {
         for (uint32_t i = 0; i < klen; ++i) put(4 + i, s.names[fd.name_off + i], true);
         put(4 + klen, 0x12, true); put(5 + klen, 0, false);
         put(6 + klen, fd.kind == K_BYTES ? 0x0A : fd.kind == K_FLOAT ? 0x12 : 0x1A, true); put(7 + klen, 0, false);
-        t.n_words = (total + 3) / 4;
+        t.n_words = (uint16_t)((total + 3) / 4); t.klen = (uint16_t)klen;
         memcpy(t.words, bytes, sizeof bytes); memcpy(t.mask, mask, sizeof mask);
       }
       CUDA_TRY(cudaMalloc(&d_templates, tp.size() * sizeof(FieldTemplate)));
@@ -277,8 +289,8 @@ struct DevSchemaBuf {
     CUDA_TRY(cudaMalloc(&d_tile_consts, tile_consts_bytes));
     CUDA_TRY(cudaMemset(d_tile_consts, 0, tile_consts_bytes));
     uint8_t* q = d_tile_consts;
-    CUDA_TRY(cudaMemcpy(q, d_tabs->s8, 8192 + 512, cudaMemcpyDeviceToDevice));      // s8 then xp512, contiguous in CrcTables
-    q += 8192 + 512 + TILE_SEEN_BYTES;
+    CUDA_TRY(cudaMemcpy(q, d_tabs->g5, TILE_CRC_BYTES, cudaMemcpyDeviceToDevice));   // g5 then xp16, contiguous in CrcTables
+    q += TILE_CRC_BYTES + TILE_SEEN_BYTES;
     if (nf) CUDA_TRY(cudaMemcpy(q, d_fields, nf * sizeof(DevField), cudaMemcpyDeviceToDevice));
     q += (nf * sizeof(DevField) + 15) & ~(size_t)15;
     if (nf) CUDA_TRY(cudaMemcpy(q, d_templates, nf * sizeof(FieldTemplate), cudaMemcpyDeviceToDevice));

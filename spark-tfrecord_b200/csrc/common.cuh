@@ -25,7 +25,12 @@ struct CrcTables {
   uint32_t k128[4][256];
   uint32_t xw[40];
   uint32_t s8[8][256];   // slicing-by-8 tables (tile.cuh: one record per thread, serial CRC from shared memory)
-  uint32_t xp512[128];   // x^(8*512*m) mod P: shifts a 512-byte segment's CRC state over m later segments
+  // tile.cuh: the 8-byte fold through 5-BIT tables.  A 32-entry table is one word per shared-memory bank, so a lookup
+  // is conflict-free whatever the 32 lanes index (a 256-entry table costs ~3 wavefronts per lookup with random bytes).
+  //   g5[k*32 + v], k = 0..12: contribution of bits 5k..5k+4 (= v) of the 64-bit block to the state 8 bytes later
+  //   g5[416 + v], g5[448 + w]: the byte-wise table split the same way, t0[x] = g5[416 + (x & 31)] ^ g5[448 + (x >> 5)]
+  uint32_t g5[512];
+  uint32_t xp16[512];    // x^(8*16*m) mod P: shifts a CRC state over m later 16-byte chunks (contiguous with g5)
 };
 #define CRC_SMEM_WORDS (256 + 1024 + 40)
 

@@ -12,7 +12,7 @@
 // implement the full semantics.  So the fast path never changes a result, it only skips work.
 //
 // Mapping: one CTA = one tile = 32 consecutive records (rows 32t .. 32t+31, contiguous in memory),
-// TILE_PARSE_WARPS parse warps + 1 CRC warp, all working on the same staged bytes.
+// TILE_PARSE_WARPS parse warps + TILE_CRC_WARPS CRC warps, all working on the same staged bytes.
 //   1. one thread arms an mbarrier and issues cp.async.bulk (TMA bulk copy, SASS UBLKCP) of the tile's
 //      byte range into shared memory; meanwhile all threads stage the slicing-by-8 CRC tables and the
 //      schema (field table + names) into shared memory.
@@ -37,7 +37,10 @@
 #ifndef TILE_PARSE_WARPS
 #define TILE_PARSE_WARPS 8
 #endif
-#define TILE_THREADS ((TILE_PARSE_WARPS + 1) * 32)
+#ifndef TILE_CRC_WARPS
+#define TILE_CRC_WARPS 4       // warps W .. W+C-1: each takes 1/C of every record's payload CRC
+#endif
+#define TILE_THREADS ((TILE_PARSE_WARPS + TILE_CRC_WARPS) * 32)
 #ifndef TILE_MIN_CTAS
 #define TILE_MIN_CTAS 3       // registers are capped so that shared memory, not the register file, limits residency
 #endif
@@ -47,7 +50,8 @@
 struct FieldTemplate {
   uint32_t words[TILE_TPL_WORDS];
   uint32_t mask[TILE_TPL_WORDS];
-  uint32_t n_words;             // 0: no template (long name): generic parse
+  uint16_t n_words;             // 0: no template (long name): generic parse
+  uint16_t klen;                // key length
   uint32_t kind;                // K_*
 };
 
@@ -57,7 +61,7 @@ struct TileArgs {
   const uint32_t* rec_off;      // [n+1]
   uint32_t n;                   // rows in the batch (stride of the scratch arrays)
   uint32_t tile_cap;            // bytes of shared memory reserved for the record bytes of one tile (TILE_ROWS slots)
-  uint32_t slot;                // bytes per record slot: an ODD multiple of 16 (bank-group spread, see crc_tile)
+  uint32_t slot;                // bytes per record slot: an ODD multiple of 16 (bank-group spread, see crc_chunks)
   uint32_t verify;
   uint32_t names_bytes;
   DevSchema sch;
@@ -156,70 +160,48 @@ __device__ __forceinline__ bool t_len(const Tile& t, uint32_t& p, uint32_t end, 
   return false;
 }
 
-// ---- per-thread CRC-32C over shared memory: slicing-by-8 with instruction-level parallelism ----
-// One 8-byte step of the register: s8 = 8 tables of 256 words.
-__device__ __forceinline__ uint32_t crc_fold8(const uint32_t* s8, uint32_t c, uint32_t lo, uint32_t hi) {
-  uint32_t a = lo ^ c;
-  return s8[7 * 256 + (a & 0xff)] ^ s8[6 * 256 + ((a >> 8) & 0xff)] ^ s8[5 * 256 + ((a >> 16) & 0xff)] ^ s8[4 * 256 + (a >> 24)] ^
-         s8[3 * 256 + (hi & 0xff)] ^ s8[2 * 256 + ((hi >> 8) & 0xff)] ^ s8[1 * 256 + ((hi >> 16) & 0xff)] ^ s8[(hi >> 24)];
+// ---- per-thread CRC-32C over shared memory: 8 bytes per step through 13 conflict-free 5-bit tables (CrcTables::g5) ----
+__device__ __forceinline__ uint32_t crc_fold8(const uint32_t* g, uint32_t c, uint32_t lo, uint32_t hi) {
+  const uint32_t a = lo ^ c;
+  return g[0 * 32 + (a & 31)] ^ g[1 * 32 + ((a >> 5) & 31)] ^ g[2 * 32 + ((a >> 10) & 31)] ^ g[3 * 32 + ((a >> 15) & 31)] ^
+         g[4 * 32 + ((a >> 20) & 31)] ^ g[5 * 32 + ((a >> 25) & 31)] ^ g[6 * 32 + (__funnelshift_r(a, hi, 30) & 31)] ^
+         g[7 * 32 + ((hi >> 3) & 31)] ^ g[8 * 32 + ((hi >> 8) & 31)] ^ g[9 * 32 + ((hi >> 13) & 31)] ^ g[10 * 32 + ((hi >> 18) & 31)] ^
+         g[11 * 32 + ((hi >> 23) & 31)] ^ g[12 * 32 + (hi >> 28)];
 }
-// CRC-32C of n bytes at tile offset o, one record per thread.
-//  * bytes up to the first 16-byte boundary go through the byte-wise table, everything after is read with aligned
-//    128-bit loads: the records of a tile sit in slots whose stride is an odd multiple of 16 bytes, so the 32 lanes
-//    of a warp spread over all eight 16-byte bank groups and a 128-bit load costs the minimum of 4 wavefronts
-//    (with 32-bit loads at a record stride of 1728 B every data load was a 16-way bank conflict).
-//  * a serial CRC is one long dependent chain (a table round trip per 8 bytes): the aligned body is cut into 512-byte
-//    segments, three segment chains run interleaved in the same thread, each segment state is shifted over the
-//    segments that follow it with ONE GF(2) multiply by the constant x^(8*512*m) (xp512), and the < 512-byte tail is
-//    folded serially from the combined state.  CRC(A||B) = CRC_B(0) ^ shift_|B|(CRC_A).
-#define CRC_SEG 512u
-__device__ __forceinline__ uint32_t crc_seg1(const uint32_t* s8, const Tile& t, uint32_t o, uint32_t c) {   // one 512-byte segment
+__device__ __forceinline__ uint32_t crc_byte(const uint32_t* g, uint32_t c, uint32_t b) {
+  const uint32_t x = (c ^ b) & 0xff;
+  return (c >> 8) ^ g[416 + (x & 31)] ^ g[448 + (x >> 5)];
+}
+// CRC-32C of a record's payload, split over the C CRC warps (lane = record, as everywhere in this kernel):
+//   head   bytes up to the first 16-byte boundary: byte-wise, by CRC warp 0, from the initial state
+//   body   K whole 16-byte chunks read with aligned 128-bit loads (the slots' stride is an odd multiple of 16 bytes, so
+//          the 32 lanes spread over all eight 16-byte bank groups and a load costs the minimum of 4 wavefronts);
+//          CRC warp c folds chunks [K*c/C, K*(c+1)/C) from state 0 (warp 0: from the head state), multiplies its state by
+//          x^(8*16*chunks after its range) (ONE GF(2) multiply by a table constant: CRC(A||B) = CRC_B(0) ^ shift_|B|(CRC_A))
+//          and XORs it into the record's accumulator in shared memory
+//   tail   < 16 bytes, folded byte-wise from the accumulated state by CRC warp 0 after the CRC warps' barrier.
+// A serial CRC is one dependent chain (a table round trip per 8 bytes) that a single warp cannot issue faster than its
+// latency allows; as one warp per tile it was the tile's critical path.
+__device__ __forceinline__ uint32_t crc_chunks(const uint32_t* g, const Tile& t, uint32_t o, uint32_t k, uint32_t c) {
 #pragma unroll 2
-  for (uint32_t i = 0; i < CRC_SEG / 16; ++i) {
+  for (uint32_t i = 0; i < k; ++i) {
     const uint4 v = t.w128(o + 16 * i);
-    c = crc_fold8(s8, c, v.x, v.y);
-    c = crc_fold8(s8, c, v.z, v.w);
+    c = crc_fold8(g, c, v.x, v.y);
+    c = crc_fold8(g, c, v.z, v.w);
   }
   return c;
 }
-__device__ __forceinline__ uint32_t crc_tile(const uint32_t* s8, const uint32_t* xp, const Tile& t, uint32_t o, uint32_t n) {
-  uint32_t c = 0xFFFFFFFFu;
-  while (n && (o & 15u)) { c = (c >> 8) ^ s8[(c ^ t.u8(o++)) & 0xff]; --n; }
-  const uint32_t nF = n / CRC_SEG;                                  // < 16: a record fits a slot of the tile
-  if (nF) {
-    uint32_t acc = 0, j = 0;
-    for (; j + 3 <= nF; j += 3) {
-      const uint32_t a = o + j * CRC_SEG;
-      uint32_t c0 = j == 0 ? c : 0u, c1 = 0, c2 = 0;
-#pragma unroll 2
-      for (uint32_t i = 0; i < CRC_SEG / 16; ++i) {
-        const uint4 v0 = t.w128(a + 16 * i), v1 = t.w128(a + CRC_SEG + 16 * i), v2 = t.w128(a + 2 * CRC_SEG + 16 * i);
-        c0 = crc_fold8(s8, c0, v0.x, v0.y); c1 = crc_fold8(s8, c1, v1.x, v1.y); c2 = crc_fold8(s8, c2, v2.x, v2.y);
-        c0 = crc_fold8(s8, c0, v0.z, v0.w); c1 = crc_fold8(s8, c1, v1.z, v1.w); c2 = crc_fold8(s8, c2, v2.z, v2.w);
-      }
-      acc ^= gf2_mulmod(xp[nF - 1 - j], c0) ^ gf2_mulmod(xp[nF - 2 - j], c1) ^ gf2_mulmod(xp[nF - 3 - j], c2);
-    }
-    for (; j < nF; ++j) acc ^= gf2_mulmod(xp[nF - 1 - j], crc_seg1(s8, t, o + j * CRC_SEG, j == 0 ? c : 0u));
-    c = acc; o += nF * CRC_SEG; n -= nF * CRC_SEG;
-  }
-  for (; n >= 16; n -= 16, o += 16) {
-    const uint4 v = t.w128(o);
-    c = crc_fold8(s8, c, v.x, v.y);
-    c = crc_fold8(s8, c, v.z, v.w);
-  }
-  while (n--) c = (c >> 8) ^ s8[(c ^ t.u8(o++)) & 0xff];
-  return ~c;
-}
 
 // shared memory layout (dynamic), all sections 16-byte aligned:
-//   [0,16) mbarrier | CRC tables 8 KiB + xp512 512 B | seen words [32][4] u32 | DevField[nf] | FieldTemplate[nf] | names | tile bytes
+//   [0,16) mbarrier | CRC tables g5 2 KiB + xp16 2 KiB | seen words [32][4] u32 + CRC accumulators [32] | DevField[nf] | FieldTemplate[nf] | names | tile bytes
 // Everything between the mbarrier and the tile is constant per schema ("consts": built once per decoder in this layout,
 // api.cu) and arrives with ONE bulk copy on the same mbarrier as the tile.
-#define TILE_SEEN_BYTES 512u
+#define TILE_SEEN_BYTES (512u + 128u)      // seen words [32][4], then the CRC accumulators [32]; zero in the consts blob
+#define TILE_CRC_BYTES (2048u + 2048u)     // g5, xp16
 __host__ __device__ inline uint32_t tile_schema_smem(uint32_t nf, uint32_t names_bytes) {
   return ((nf * (uint32_t)sizeof(DevField) + 15u) & ~15u) + ((nf * (uint32_t)sizeof(FieldTemplate) + 15u) & ~15u) + ((names_bytes + 15u) & ~15u);
 }
-__host__ __device__ inline uint32_t tile_const_bytes(uint32_t nf, uint32_t names_bytes) { return 8192 + 512 + TILE_SEEN_BYTES + tile_schema_smem(nf, names_bytes); }
+__host__ __device__ inline uint32_t tile_const_bytes(uint32_t nf, uint32_t names_bytes) { return TILE_CRC_BYTES + TILE_SEEN_BYTES + tile_schema_smem(nf, names_bytes); }
 __host__ __device__ inline uint32_t tile_smem_bytes(uint32_t nf, uint32_t names_bytes, uint32_t tile_cap) {
   return 16 + tile_const_bytes(nf, names_bytes) + tile_cap + 64;   // +64: template compares may look a few bytes past the tile
 }
@@ -228,10 +210,10 @@ template <bool SEQ>
 __global__ void __launch_bounds__(TILE_THREADS, TILE_MIN_CTAS) decode_tile_kernel(TileArgs A) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
-  uint32_t* s8 = reinterpret_cast<uint32_t*>(smem_raw + 16);                               // 8 KiB
-  uint32_t* sseen = reinterpret_cast<uint32_t*>(smem_raw + 16 + 8192 + 512);                 // [32 rows][4 words], zero in the consts blob
+  uint32_t* s8 = reinterpret_cast<uint32_t*>(smem_raw + 16);                               // g5 tables, then xp512
+  uint32_t* sseen = reinterpret_cast<uint32_t*>(smem_raw + 16 + TILE_CRC_BYTES);                 // [32 rows][4 words], zero in the consts blob
   const uint32_t nf = (uint32_t)A.sch.n_fields;
-  uint8_t* sbase = smem_raw + 16 + 8192 + 512 + TILE_SEEN_BYTES;
+  uint8_t* sbase = smem_raw + 16 + TILE_CRC_BYTES + TILE_SEEN_BYTES;
   DevField* sfields = reinterpret_cast<DevField*>(sbase);
   FieldTemplate* stpl = reinterpret_cast<FieldTemplate*>(sbase + ((nf * (uint32_t)sizeof(DevField) + 15u) & ~15u));
   uint8_t* snames = sbase + ((nf * (uint32_t)sizeof(DevField) + 15u) & ~15u) + ((nf * (uint32_t)sizeof(FieldTemplate) + 15u) & ~15u);
@@ -287,20 +269,41 @@ __global__ void __launch_bounds__(TILE_THREADS, TILE_MIN_CTAS) decode_tile_kerne
   T.b = tile_b;
   asm volatile("mov.u32 %0, %1;" : "=r"(T.s) : "r"(smem_u32(tile_b)) : "memory");   // ordered after mbar_wait
 
-  // =============================== last warp: CRC ===============================
-  if (wid == TILE_PARSE_WARPS) {
-    if (active && A.verify) {
-      // the frame index chained the headers without checking them on the fast path: check the length CRC here
-      if (crc_mask(crc_u64(s8, t_u32(T, pay - 12), t_u32(T, pay - 8))) != t_u32(T, pay - 4)) atomicOr(A.flags, TF_FALLBACK);
-      uint32_t crc = crc_tile(s8, s8 + 2048, T, pay, len);
-      if (crc_mask(crc) != t_u32(T, end)) atomicOr(A.flags, TF_FALLBACK);      // the general path reports the error at the right record
+  // =============================== warps W .. W+C-1: CRC ===============================
+  if (wid >= TILE_PARSE_WARPS) {
+    const uint32_t cw = wid - TILE_PARSE_WARPS;
+    uint32_t* scrc = sseen + 128;
+    const uint32_t* xp16 = s8 + 512;
+    const bool on = active && A.verify;
+    const uint32_t hn = min(len, (0u - pay) & 15u);
+    const uint32_t b0 = pay + hn;                                  // 16-byte aligned, or the end of a tiny payload
+    const uint32_t K = (end - b0) >> 4;
+    if (on) {
+      uint32_t c = 0;
+      if (cw == 0) {
+        c = 0xFFFFFFFFu;
+        for (uint32_t i = 0; i < hn; ++i) c = crc_byte(s8, c, T.u8(pay + i));
+      }
+      if (cw == TILE_CRC_WARPS - 1) {
+        // the frame index chained the headers without checking them on the fast path: check the length CRC here
+        if (crc_mask(~crc_fold8(s8, 0xFFFFFFFFu, t_u32(T, pay - 12), t_u32(T, pay - 8))) != t_u32(T, pay - 4)) atomicOr(A.flags, TF_FALLBACK);
+      }
+      const uint32_t k0 = K * cw / TILE_CRC_WARPS, k1 = K * (cw + 1) / TILE_CRC_WARPS;
+      c = crc_chunks(s8, T, b0 + 16 * k0, k1 - k0, c);
+      if (c) atomicXor(&scrc[lane], K - k1 ? gf2_mulmod(xp16[K - k1], c) : c);
+    }
+    asm volatile("bar.sync 2, %0;" ::"r"(TILE_CRC_WARPS * 32) : "memory");
+    if (cw == 0 && on) {
+      uint32_t c = scrc[lane];
+      for (uint32_t o = b0 + 16 * K; o < end; ++o) c = crc_byte(s8, c, T.u8(o));
+      if (crc_mask(~c) != t_u32(T, end)) atomicOr(A.flags, TF_FALLBACK);        // the general path reports the error at the right record
     }
     return;
   }
 
   // =============================== warps 0..W-1: parse ===============================
   bool bad = false;
-  uint32_t entry_idx = 0;
+  uint32_t skip = wid;                     // entries to hop before the next one this warp owns (entry index % W == wid)
   uint32_t shape_bad = 0;
   unsigned long long seen_lo = 0, seen_hi = 0;
   if (active) {
@@ -324,9 +327,6 @@ __global__ void __launch_bounds__(TILE_THREADS, TILE_MIN_CTAS) decode_tile_kerne
       // hop over the entries the other parse warps own (`0A elen ...`): a tight loop, one byte load + add per entry.
       // The owner validates those entries; p + 1 <= cend is always inside the tile and an overshoot is caught by the
       // p == cend check after the loop.
-      const uint32_t er = entry_idx % TILE_PARSE_WARPS;
-      uint32_t skip = wid >= er ? wid - er : wid + TILE_PARSE_WARPS - er;
-      entry_idx += skip;
       for (bool wide = true; wide;) {
         wide = false;
         while (skip && p < cend) {                           // the tight part: single-byte entry lengths only
@@ -342,30 +342,40 @@ __global__ void __launch_bounds__(TILE_THREADS, TILE_MIN_CTAS) decode_tile_kerne
           --skip;
         }
       }
-      entry_idx -= skip;                                     // hops not performed (ran into cend)
       if (bad || p >= cend) break;
-      ++entry_idx;                                           // the entry this warp owns
+      skip = TILE_PARSE_WARPS - 1;                           // this entry is ours; W - 1 hops to the next
       // ---- owned entry: try the expected field's template first ----
-      uint32_t eend, vlen;
+      uint32_t eend, kind, llen;
       int f = -1;
       bool located = false;
       if (next_f < nf && stpl[next_f].n_words) {
         const FieldTemplate& tp = stpl[next_f];
-        const uint32_t klen = sfields[next_f].name_len;
-        uint32_t diff = 0;
+        const uint32_t klen = tp.klen;
+        // the entry's first 20 bytes as 5 words at any alignment: 6 aligned loads + funnel shifts (words past the template
+        // have an all-zero mask)
+        const uint32_t ab = p & ~3u, sh = (p & 3u) * 8;
+        uint32_t aw[TILE_TPL_WORDS + 1];
 #pragma unroll
-        for (int w = 0; w < TILE_TPL_WORDS; ++w)
-          if ((uint32_t)w < tp.n_words) diff |= (t_u32(T, p + 4 * w) ^ tp.words[w]) & tp.mask[w];
-        const uint32_t elen = T.u8(p + 1), vl = T.u8(p + 5 + klen), ll = T.u8(p + 7 + klen);
-        // single-byte lengths that nest exactly: entry = key part (klen+2) + 2 + value; value = 2 + list
+        for (int w = 0; w <= TILE_TPL_WORDS; ++w) aw[w] = T.w32(ab + 4 * w);
+        uint32_t diff = 0, u0 = 0;
+#pragma unroll
+        for (int w = 0; w < TILE_TPL_WORDS; ++w) {
+          const uint32_t u = __funnelshift_r(aw[w], aw[w + 1], sh);
+          if (w == 0) u0 = u;
+          diff |= (u ^ tp.words[w]) & tp.mask[w];
+        }
+        const uint32_t elen = (u0 >> 8) & 0xff, vl = T.u8(p + 5 + klen), ll = T.u8(p + 7 + klen);
+        // single-byte lengths that nest exactly: entry = key part (klen+2) + 2 + value; value = 2 + list.  The template
+        // covers the kind tag, so the Feature's oneof member is already known to be the one the schema wants.
         if (diff == 0 && elen < 0x80 && elen == klen + 4 + vl && vl == ll + 2 && p + 2 + elen <= cend) {
-          f = (int)next_f; eend = p + 2 + elen; vlen = vl; located = true;
-          p += klen + 6;                                      // at the kind tag
+          f = (int)next_f; eend = p + 2 + elen; located = true;
+          kind = tp.kind; llen = ll;
+          p += klen + 8;                                      // at the list body
         }
       }
       if (!located) {
         // ---- generic: 0A elen 0A klen key 12 vlen, key looked up by hash ----
-        uint32_t elen, klen;
+        uint32_t elen, klen, vlen;
         if (T.u8(p) != 0x0A) { bad = true; break; }
         ++p;
         if (!t_len(T, p, cend, elen) || cend - p < elen) { bad = true; break; }
@@ -394,21 +404,29 @@ __global__ void __launch_bounds__(TILE_THREADS, TILE_MIN_CTAS) decode_tile_kerne
           }
           slot = (slot + 1) & (uint32_t)A.sch.ht_mask;
         }
+        if (f >= 0 && sfields[f].elem_type == TFR_T_NULL) f = -1;               // NullType: always null, value only validated
+        // ---- Feature: exactly one oneof member spanning the value ----
+        if (vlen == 0) { if (f >= 0) bad = true; p = eend; continue; }            // kind not set: an error if the schema wants it
+        const uint32_t kt = T.u8(p++);
+        kind = kt == 0x0A ? K_BYTES : kt == 0x12 ? K_FLOAT : kt == 0x1A ? K_INT64 : K_NONE;
+        if (kind == K_NONE || !t_len(T, p, eend, llen) || p + llen != eend) { bad = true; break; }
+        if (f >= 0 && (uint32_t)sfields[f].kind != kind) { bad = true; break; }   // kind mismatch: error path
       }
-      if (f >= 0 && sfields[f].elem_type == TFR_T_NULL) f = -1;                 // NullType: always null, value only validated
-      if (f >= 0) {
-        unsigned long long bit = 1ull << (f & 63);
-        if (f < 64) { if (seen_lo & bit) { bad = true; break; } seen_lo |= bit; }    // duplicate key (inside this warp's entries)
-        else { if (seen_hi & bit) { bad = true; break; } seen_hi |= bit; }
-        next_f = (uint32_t)f + TILE_PARSE_WARPS;
-      }
-      // ---- Feature: exactly one oneof member spanning the value ----
-      if (vlen == 0) { if (f >= 0) bad = true; p = eend; continue; }              // kind not set: an error if the schema wants it
-      uint32_t kt = T.u8(p++), llen;
-      uint32_t kind = kt == 0x0A ? K_BYTES : kt == 0x12 ? K_FLOAT : kt == 0x1A ? K_INT64 : K_NONE;
-      if (kind == K_NONE || !t_len(T, p, eend, llen) || p + llen != eend) { bad = true; break; }
       const DevField* fd = f >= 0 ? &sfields[f] : nullptr;
-      if (fd && ((uint32_t)fd->kind != kind || fd->depth > 1)) { bad = true; break; }   // kind mismatch / nesting: error path
+      if (fd) {
+        const uint32_t bit = 1u << (f & 31);                                      // duplicate key (inside this warp's entries)
+        if (f < 64) {
+          const unsigned long long b64 = (unsigned long long)bit << (f & 32);
+          if (seen_lo & b64) { bad = true; break; }
+          seen_lo |= b64;
+        } else {
+          const unsigned long long b64 = (unsigned long long)bit << (f & 32);
+          if (seen_hi & b64) { bad = true; break; }
+          seen_hi |= b64;
+        }
+        next_f = (uint32_t)f + TILE_PARSE_WARPS;
+        if (fd->depth > 1) { bad = true; break; }                                 // nesting in a Feature: error path
+      }
       if (kind == K_BYTES) {
         // BytesList: { 0A blen bytes }*
         uint32_t n = 0, first_off = 0, first_len = 0, first_data = 0, total = 0;
@@ -476,14 +494,25 @@ __global__ void __launch_bounds__(TILE_THREADS, TILE_MIN_CTAS) decode_tile_kerne
           if (plen & 3) { bad = true; break; }
           n = plen >> 2;
         } else {
-          // varints: count terminators, every run <= 10 bytes, the last byte terminates; first value decoded on the way
+          // varints: count terminators, every run <= 10 bytes, the last byte terminates; first value decoded on the way.
+          // Up to 8 bytes are handled in registers: terminator bits by mask, the first varint's 7-bit groups compacted
+          // with three shift-and-mask rounds.
           n = 0;
-          uint32_t run = 0;
-          if (plen == 1) {                                   // the most common case: one small value
-            v0 = T.u8(pk);
-            if (v0 & 0x80) { bad = true; break; }
-            n = 1;
+          if (plen >= 1 && plen <= 8) {
+            const uint32_t w0 = t_u32(T, pk), w1 = plen > 4 ? t_u32(T, pk + 4) : 0u;
+            unsigned long long x = ((unsigned long long)w1 << 32) | w0;
+            const unsigned long long live = ~0ull >> (64 - 8 * plen);
+            const unsigned long long term = ~x & 0x8080808080808080ull & live;          // MSB clear: a varint ends here
+            if (!((term >> (8 * plen - 1)) & 1)) { bad = true; break; }                 // the last byte must terminate
+            n = (uint32_t)__popcll(term);
+            const uint32_t k0 = (uint32_t)__ffsll((long long)term);                     // 8 * length of the first varint
+            x &= (~0ull >> (64 - k0)) & 0x7f7f7f7f7f7f7f7full;
+            x = ((x & 0x7f007f007f007f00ull) >> 1) | (x & 0x007f007f007f007full);
+            x = ((x & 0x3fff00003fff0000ull) >> 2) | (x & 0x00003fff00003fffull);
+            x = ((x & 0x0fffffff00000000ull) >> 4) | (x & 0x000000000fffffffull);
+            v0 = x;
           } else {
+            uint32_t run = 0;
             for (uint32_t i = 0; i < plen; ++i) {
               uint32_t b = T.u8(pk + i);
               if (n == 0) v0 |= (uint64_t)(b & 0x7f) << (7 * run);
@@ -545,10 +574,7 @@ __global__ void __launch_bounds__(TILE_THREADS, TILE_MIN_CTAS) decode_tile_kerne
     // ---- SequenceExample.feature_lists: { 0A elen 0A klen key 12 vlen FeatureList }*, FeatureList = { 0A flen Feature }* ----
     p = fl_start;
     while (SEQ && !bad && p < fl_end) {
-      const uint32_t er = entry_idx % TILE_PARSE_WARPS;
-      uint32_t skip = wid >= er ? wid - er : wid + TILE_PARSE_WARPS - er;
       while (skip && p < fl_end) {
-        ++entry_idx;
         const uint32_t b1 = T.u8(p + 1);
         if (b1 < 0x80) p += 2 + b1;
         else {
@@ -559,7 +585,7 @@ __global__ void __launch_bounds__(TILE_THREADS, TILE_MIN_CTAS) decode_tile_kerne
         --skip;
       }
       if (bad || p >= fl_end) break;
-      ++entry_idx;                                           // the entry this warp owns
+      skip = TILE_PARSE_WARPS - 1;                           // the entry this warp owns
       uint32_t elen, klen, vlen;
       if (T.u8(p) != 0x0A) { bad = true; break; }
       ++p;
