@@ -35,10 +35,10 @@
 
 #define TILE_ROWS 32
 #ifndef TILE_PARSE_WARPS
-#define TILE_PARSE_WARPS 8
+#define TILE_PARSE_WARPS 12
 #endif
 #ifndef TILE_CRC_WARPS
-#define TILE_CRC_WARPS 4       // warps W .. W+C-1: each takes 1/C of every record's payload CRC
+#define TILE_CRC_WARPS 3       // warps W .. W+C-1: each takes 1/C of every record's payload CRC
 #endif
 #define TILE_THREADS ((TILE_PARSE_WARPS + TILE_CRC_WARPS) * 32)
 #ifndef TILE_MIN_CTAS
