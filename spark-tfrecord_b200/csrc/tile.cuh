@@ -13,16 +13,18 @@
 //
 // Mapping: one CTA = one tile = 32 consecutive records (rows 32t .. 32t+31, contiguous in memory),
 // TILE_PARSE_WARPS parse warps + TILE_CRC_WARPS CRC warps, all working on the same staged bytes.
-//   1. one thread arms an mbarrier and issues cp.async.bulk (TMA bulk copy, SASS UBLKCP) of the tile's
-//      byte range into shared memory; meanwhile all threads stage the slicing-by-8 CRC tables and the
-//      schema (field table + names) into shared memory.
-//   2. role split over the same staged bytes: the last warp computes the masked CRC-32C of record `lane`
-//      (serial slicing-by-8, 8 bytes per step); parse warp w owns the map entries with index = w mod W of
-//      record `lane`: it fully parses those and only hops over the others (`0A elen` -> p += elen).  An
-//      owned entry is first matched against a per-field TEMPLATE of its constant bytes
-//      (0A ? 0A klen key 12 ? kind ?: a few masked word compares); only when that fails is it parsed
-//      byte by byte (hash lookup of the key, full checks).  Shared-memory capacity limits how many
-//      records an SM can stage, so more dependent-chains per staged record = more warps to hide latency.
+//   1. warp 0 arms an mbarrier; every lane issues cp.async.bulk (TMA bulk copy, SASS UBLKCP) of ITS record into its
+//      own slot of the tile (slot stride = an odd multiple of 16 bytes: the lanes' records spread over all eight
+//      16-byte bank groups), and one more bulk copy brings the per-schema constants (5-bit CRC tables, zeroed merge
+//      words, field table, entry templates, names), which api.cu keeps in HBM in exactly the shared-memory layout.
+//   2. role split over the same staged bytes: the C CRC warps each fold a third of the 16-byte chunks of record
+//      `lane` (aligned 128-bit loads, 13 conflict-free 5-bit table lookups per 8 bytes) and combine through one GF(2)
+//      shift each; parse warp w owns the map entries with index = w mod W of record `lane`: it fully parses those and
+//      only hops over the others (`0A elen` -> p += elen).  An owned entry is first matched against a per-field
+//      TEMPLATE of its constant bytes (0A ? 0A klen key 12 ? kind ?: masked word compares), which also fixes the
+//      Feature kind and list length; only when that fails is it parsed byte by byte (hash lookup of the key, full
+//      checks).  Shared-memory capacity limits how many records an SM can stage, so more dependent chains per staged
+//      record = more warps to hide latency, and no single warp's chain is the tile's critical path.
 //   3. lane = row, rows are 32-aligned: every column store of the warp covers 32 consecutive rows
 //      (coalesced by construction, no transpose) and validity bitmaps are one __ballot_sync per field.
 //   4. variable-width columns either write element counts + source offsets (scan + decode_pass2_kernel
