@@ -66,6 +66,20 @@ __device__ __forceinline__ uint32_t frame_chain(const uint32_t* t0, const uint8_
     if ((uint64_t)left < 16ull + lo) return FS_PART_REC;
     if (stage && count < FRAME_STAGE) stage[count] = q;
     q += 16 + lo;
+#ifndef FRAME_NO_PREFETCH
+    // the chain is a DRAM-latency-bound pointer chase; records of a file tend to have similar sizes, so the headers two
+    // and three records ahead are probably near q + k*(16 + lo): ask L2 for those lines now
+    {
+      const uint32_t step = 16 + lo;
+      if (step < 0x100000u) {
+        const uint32_t a1 = q + step, a2 = a1 + step;
+        if (a2 + 64 < nbytes) {
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(data + a1));
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(data + a2));
+        }
+      }
+    }
+#endif
     max_len = max(max_len, lo);
     ++count;
   }
