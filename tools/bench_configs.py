@@ -73,6 +73,11 @@ b.release()
 def run4():
     b, used = dec.decode(d4); b.wait(); b.release()
 t = timeit(run4)
+dec.set_profiling(True)
+for _ in range(5): run4()
+prof4 = dec.get_profile()
+dec.set_profiling(False)
+res["cfg4_stage_ms_5_steps"] = prof4
 res["cfg4_seqexample_decode"] = {"records": n4, "framed_bytes": len(data4), "mean_record_bytes": len(data4) / n4, "ms": 1e3 * t, "GBps_in": len(data4) / t / 1e9,
                                  "parity": "bit-exact vs source columns (all rows)"}
 dec.close()
