@@ -16,6 +16,7 @@
 #include "common.cuh"
 #include "decode.cuh"
 #include "encode.cuh"
+#include "encode_tile.cuh"
 #include "frame.cuh"
 #include "host_util.h"
 #include "infer.cuh"

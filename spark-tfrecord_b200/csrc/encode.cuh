@@ -225,7 +225,7 @@ __global__ void __launch_bounds__(256) encode_kernel(EncodeArgs A) {
     uint32_t plen = 1 + vsize32(gsize[0]) + gsize[0] + (seq ? 1 + vsize32(gsize[1]) + gsize[1] : 0);
     if (MODE == 0) {
       if (__any_sync(FULLMASK, null_err) && lane == 0) atomicMin(A.first_null_err, row);
-      if (lane == 0) A.rec_size[row] = 16 + plen;
+      if (lane == 0) { A.rec_size[row] = 16 + plen; atomicMax(A.first_null_err + 4, 16 + plen); }   // [4]: largest framed record (encode_tile.cuh slot)
       continue;
     }
     uint8_t* rec = A.out + A.rec_off[row];
