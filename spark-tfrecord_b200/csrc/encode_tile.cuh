@@ -42,6 +42,45 @@ __host__ __device__ inline uint32_t enc_tile_smem_bytes(uint32_t nf, uint32_t sl
   return 4096 + 128 + 128 + ((nf * 32 * 2 * 2 + 15u) & ~15u) + ENC_TILE_ROWS * slot + 16;
 }
 
+// size pass with the same mapping (lane = row, warp w takes fields w, w+W, ...): coalesced column reads, Feature sizes
+// written [field][row], record sizes accumulated per row in shared memory.  Replaces encode_kernel<0> for Example schemas.
+struct EncSizeArgs {
+  DevSchema sch;
+  const EncCol* cols;
+  uint32_t n_rows;
+  uint32_t* rec_size;           // [n_rows]
+  uint32_t* cell_size;          // [n_fields][n_rows]
+  uint32_t* small;              // [0] atomicMin first row with a null in a non-nullable column, [4] atomicMax framed record size
+};
+__global__ void __launch_bounds__(ENC_TILE_THREADS) encode_tile_size_kernel(EncSizeArgs A) {
+  __shared__ uint32_t sacc[ENC_TILE_ROWS];
+  const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const uint32_t nf = (uint32_t)A.sch.n_fields;
+  const uint32_t row = blockIdx.x * ENC_TILE_ROWS + lane;
+  const bool active = row < A.n_rows;
+  if (threadIdx.x < ENC_TILE_ROWS) sacc[threadIdx.x] = 0;
+  __syncthreads();
+  uint32_t sum = 0;
+  bool null_err = false;
+  if (active)
+    for (uint32_t f = wid; f < nf; f += ENC_TILE_WARPS) {
+      const DevField& fd = A.sch.fields[f];
+      const uint32_t V = cell_value_size(fd, A.cols[f], row);
+      A.cell_size[(size_t)f * A.n_rows + row] = V;
+      if (V == 0xffffffffu) { if (!fd.nullable) null_err = true; }      // NullPointerException (:29-31)
+      else sum += entry_total(fd, V);
+    }
+  if (sum) atomicAdd(&sacc[lane], sum);
+  if (null_err) atomicMin(A.small, row);
+  __syncthreads();
+  if (wid == 0 && active) {
+    const uint32_t G = sacc[lane], sz = 16 + 1 + vsize32(G) + G;
+    A.rec_size[row] = sz;
+    const uint32_t mx = __reduce_max_sync(__activemask(), sz);
+    if (lane == 0) atomicMax(A.small + 4, mx);
+  }
+}
+
 __global__ void __launch_bounds__(ENC_TILE_THREADS, 3) encode_tile_kernel(EncTileArgs A) {
   extern __shared__ __align__(128) uint8_t esm[];
   uint32_t* g5 = reinterpret_cast<uint32_t*>(esm);
