@@ -117,7 +117,8 @@ int32_t tfr_decoder_staging(tfr_decoder*, size_t min_bytes, void** host_ptr, siz
  * deserializeExample (M/TFRecordFileReader.scala:49-81, M/TFRecordDeserializer.scala:21-61).
  *   data/nbytes : framed TFRecord bytes (u64 len | u32 maskedcrc(len) | payload | u32 maskedcrc)
  *                 starting at a record boundary; in host memory (pageable or the pinned
- *                 staging above) or in device memory (data_on_device != 0).
+ *                 staging above) or in device memory (data_on_device != 0; any alignment is
+ *                 accepted, a 16-byte aligned pointer gets the single-pass tile kernels).
  *   is_final    : nonzero -> a trailing partial record is TFR_E_TRUNCATED (EOF inside a
  *                 record); zero -> it is left unconsumed (see *consumed).
  * Work is enqueued on the decoder's stream; the call returns after the stage that needs

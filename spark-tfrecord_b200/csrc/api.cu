@@ -766,7 +766,9 @@ static int32_t decode_impl(tfr_decoder* d, const void* data, size_t nbytes, int3
     k1_verified = verify_headers || !C.verify;
     return TFR_OK;
   };
-  const bool try_fast = allow_fast && d->fast_ok;
+  // the tile kernel's bulk copies need 16-byte aligned global addresses: a device buffer at any other alignment is legal
+  // input but takes the general path
+  const bool try_fast = allow_fast && d->fast_ok && (reinterpret_cast<uintptr_t>(C.d_data) & 15u) == 0;
   if (nbytes) TRY(run_k1(!try_fast));
   if (nbytes && !k1_verified && frame_stop_to_error(fr.stop, is_final != 0) != TFR_OK) TRY(run_k1(true));   // a framing problem: get the exact verdict
   const uint32_t n = C.n;

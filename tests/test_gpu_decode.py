@@ -248,3 +248,46 @@ def test_path_variants_agree(native, oracle, env, monkeypatch):
             assert_columns_equal(b.to_host(), cols, sch.names, str(env))
             b.release()
         dec.close()
+
+
+def test_device_input_at_every_alignment(native, oracle):
+    """a device buffer at any byte alignment is legal input (only 16-byte aligned ones take the tile kernels)"""
+    import torch
+    from oracle.corpus import cfg2_columns
+    sch, cols = cfg2_columns(700, seed=41)
+    data, rc, _ = oracle.encode(cols, sch)
+    want = oracle.decode(data, sch)
+    dec = native.Decoder(sch)
+    try:
+        for shift in (0, 1, 3, 4, 8, 15, 16):
+            buf = torch.zeros(len(data) + 64, dtype=torch.uint8, device="cuda")
+            view = buf[shift:shift + len(data)]
+            view.copy_(torch.frombuffer(bytearray(data), dtype=torch.uint8))
+            for _ in range(2):                                   # second call: uniform-shape speculation
+                batch, used = dec.decode(view)
+                assert used == len(data) and batch.info["error_code"] == 0
+                assert_columns_equal(batch.to_host(), want.columns, sch.names, f"shift {shift}")
+                batch.release()
+    finally:
+        dec.close()
+
+
+def test_tile_slot_shapes(native, oracle):
+    """record sizes around the tile kernel's slot geometry: tiny payloads (no 16-byte chunk), payloads that end on every
+    residue mod 16, one long record among short ones (slot stride follows the longest), Int64 varints of every width"""
+    rng = np.random.default_rng(77)
+    sch = StructType([StructField("a", LongType()), StructField("s", BinaryType()), StructField("v", ArrayType(LongType()))])
+    rows = []
+    for i in range(400):
+        width = i % 11                                           # 0: small value; k: a value that needs k varint bytes
+        a = int(rng.integers(0, 100)) if width == 0 else (-(i + 1) if width == 10 else int(1 << (7 * width - 1)) + i)
+        s = rng.integers(0, 256, i % 53, dtype=np.uint8).tobytes()
+        v = [int(x) for x in rng.integers(-2**62, 2**62, i % 5)]
+        rows.append((a, s, v))
+    rows.append((7, rng.integers(0, 256, 5000, dtype=np.uint8).tobytes(), list(range(300))))      # one long record
+    rows += [(1, b"", []), (2, b"x", [0])] * 20
+    cols = A.columns_from_rows(sch, rows)
+    _roundtrip(native, oracle, sch, cols, tag="slot shapes")
+    # a single field: payloads of a few bytes only
+    sch1 = StructType([StructField("a", LongType())])
+    _roundtrip(native, oracle, sch1, A.columns_from_rows(sch1, [(i,) for i in range(100)]), tag="tiny payloads")

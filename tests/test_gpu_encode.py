@@ -180,3 +180,36 @@ def test_many_fields_more_than_a_warp(native, oracle):
     cols = A.columns_from_rows(sch, rows)
     got, back = _check(native, oracle, sch, cols)
     assert_columns_equal(back, cols, sch.names, "100 fields")
+
+
+def test_tile_emit_shapes(native, oracle):
+    """the tile emit kernel: row counts around the 32-row tile, nulls, empty lists and strings, one long row among
+    short ones, every Int64 varint width; and the same bytes through the general kernel"""
+    import os
+    rng = np.random.default_rng(5)
+    sch = StructType([StructField("a", LongType()), StructField("i", IntegerType()), StructField("f", ArrayType(FloatType())),
+                      StructField("d", DoubleType()), StructField("s", StringType()), StructField("b", ArrayType(BinaryType())),
+                      StructField("v", ArrayType(LongType()))])
+    def row(i):
+        width = i % 11
+        a = None if i % 13 == 5 else (int(rng.integers(0, 100)) if width == 0 else (-(i + 1) if width == 10 else int(1 << (7 * width - 1)) + i))
+        f = None if i % 17 == 3 else [float(x) for x in rng.standard_normal(i % 9).astype(np.float32)]
+        s = None if i % 19 == 7 else "".join(chr(97 + (i + k) % 26) for k in range(i % 31))
+        b = [rng.integers(0, 256, (i + k) % 7, dtype=np.uint8).tobytes() for k in range(i % 4)]
+        v = [int(x) for x in rng.integers(-2**62, 2**62, i % 5)]
+        return (a, int(rng.integers(-2**31, 2**31)), f, float(rng.standard_normal()), s, b, v)
+    for n in (1, 31, 32, 33, 64, 257):
+        rows = [row(i) for i in range(n)]
+        if n == 257:
+            rows[100] = (1, 2, [1.0] * 900, 3.0, "y" * 2500, [b"z" * 700], list(range(200)))
+        cols = A.columns_from_rows(sch, rows)
+        want, rc, _ = oracle.encode(cols, sch, 0)
+        assert rc == 0
+        got = gpu_encode(native, sch, cols, 0)
+        assert got == want, _diff(got, want)
+        os.environ["TFR_DISABLE_FAST"] = "1"
+        try:
+            got2 = gpu_encode(native, sch, cols, 0)
+        finally:
+            del os.environ["TFR_DISABLE_FAST"]
+        assert got2 == want, _diff(got2, want)
