@@ -40,6 +40,104 @@ def _record_type(options: Optional[Dict[str, str]]) -> int:
     return RECORD_TYPES[rt]
 
 
+# ---- stream compression: host-side, around the same GPU kernels -------------------------------------------
+# The reference hands `codec` to Hadoop (M/DefaultSource.scala:94-102: a codec class name) and CodecStreams compresses the
+# whole output stream; on read, Hadoop picks the codec from the file extension.  The compressed bytes are a container
+# around the framed records, so they are (de)compressed on the host and the framed bytes go through the C ABI unchanged.
+_CODECS = {   # name -> (file extension, Hadoop class)
+    "gzip": (".gz", "org.apache.hadoop.io.compress.GzipCodec"),
+    "deflate": (".deflate", "org.apache.hadoop.io.compress.DefaultCodec"),
+    "bzip2": (".bz2", "org.apache.hadoop.io.compress.BZip2Codec"),
+}
+
+
+def _codec_name(codec: str) -> Optional[str]:
+    """option value (Hadoop class name, or its short name) -> one of _CODECS; '' -> None"""
+    if not codec:
+        return None
+    for name, (_, cls) in _CODECS.items():
+        if codec == cls or codec.lower() == name or codec.lower() == cls.rsplit(".", 1)[1].lower():
+            return name
+    raise _native.IllegalArgumentException(-3, f"codec {codec}: only GzipCodec, DefaultCodec (deflate) and BZip2Codec are available on this host")
+
+
+def _codec_of_path(path: str) -> Optional[str]:
+    for name, (ext, _) in _CODECS.items():
+        if path.endswith(ext):
+            return name
+    return None
+
+
+class _DeflateReader:
+    """zlib-format stream (Hadoop DefaultCodec, '.deflate') as a file-like object with read(n)"""
+
+    def __init__(self, f):
+        import zlib
+        self._f, self._z, self._buf, self._eof = f, zlib.decompressobj(), b"", False
+
+    def read(self, n: int = -1) -> bytes:
+        while not self._eof and (n < 0 or len(self._buf) < n):
+            raw = self._f.read(1 << 20)
+            if not raw:
+                self._buf += self._z.flush()
+                self._eof = True
+                break
+            self._buf += self._z.decompress(raw)
+        if n < 0:
+            out, self._buf = self._buf, b""
+        else:
+            out, self._buf = self._buf[:n], self._buf[n:]
+        return out
+
+    def close(self):
+        self._f.close()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+
+class _DeflateWriter:
+    def __init__(self, f):
+        import zlib
+        self._f, self._z = f, zlib.compressobj()
+
+    def write(self, b: bytes):
+        self._f.write(self._z.compress(b))
+
+    def close(self):
+        self._f.write(self._z.flush())
+        self._f.close()
+
+
+def _open_read(path: str):
+    """file object yielding the FRAMED bytes of `path` (decompressed when the extension names a codec)"""
+    codec = _codec_of_path(path)
+    if codec == "gzip":
+        import gzip
+        return gzip.open(path, "rb")
+    if codec == "bzip2":
+        import bz2
+        return bz2.open(path, "rb")
+    if codec == "deflate":
+        return _DeflateReader(open(path, "rb"))
+    return open(path, "rb")
+
+
+def _open_write(path: str, codec: Optional[str]):
+    if codec == "gzip":
+        import gzip
+        return gzip.open(path, "wb")
+    if codec == "bzip2":
+        import bz2
+        return bz2.open(path, "wb")
+    if codec == "deflate":
+        return _DeflateWriter(open(path, "wb"))
+    return open(path, "wb")
+
+
 def _rows_of(batch: "_native.Batch") -> List[tuple]:
     cols = batch.to_host()
     return [tuple(c.get(r) for c in cols) for r in range(batch.n_rows)]
@@ -144,9 +242,11 @@ class TFRecordFileReader:
 
         def gen():
             try:
-                with open(file.toPath(), "rb") as f:
-                    f.seek(file.start)
-                    remaining = file.length
+                compressed = _codec_of_path(file.toPath()) is not None
+                with _open_read(file.toPath()) as f:
+                    if not compressed:
+                        f.seek(file.start)
+                    remaining = (1 << 62) if compressed else file.length          # a compressed file is read to its end
                     carry = b""
                     while True:
                         want = min(max(block - len(carry), block // 2), remaining)   # a carried record larger than the block still makes progress
@@ -184,7 +284,7 @@ class TFRecordOutputWriter:
         self.schema = byte_array_schema() if self.recordType == 2 else dataSchema
         self._enc = _native.Encoder(self.schema, self.recordType, device)
         self._rows: List[tuple] = []
-        self._out = open(path, "wb")                            # CodecStreams.createOutputStream (no codec here)
+        self._out = _open_write(path, _codec_name((options or {}).get("codec", "")))   # CodecStreams.createOutputStream (:19)
 
     def write(self, row: Sequence) -> None:
         self._rows.append(tuple(row))
@@ -231,7 +331,7 @@ class DefaultSource:
         inf = _native.Infer(rt, device)
         try:
             for f in todo:
-                with open(f, "rb") as fh:
+                with _open_read(f) as fh:
                     inf.update(fh.read())
             local = inf.result()
         finally:
@@ -243,16 +343,14 @@ class DefaultSource:
         return lambda file: TFRecordFileReader.readFile(None, options, file, requiredSchema, device)
 
     def prepareWrite(self, options: Dict[str, str], dataSchema: StructType):
-        codec = (options or {}).get("codec", "")
-        if codec:
-            raise NotImplementedError("codec: stream compression stays on the JVM side (CodecStreams), out of scope here")
+        codec = _codec_name((options or {}).get("codec", ""))             # :94-102: the option turns output compression on
 
         class _Factory:
             def newInstance(self_inner, path, schema, context=None):
                 return TFRecordOutputWriter(path, options, schema, context)
 
-            def getFileExtension(self_inner, context=None):
-                return ".tfrecord"
+            def getFileExtension(self_inner, context=None):                 # :110-112
+                return ".tfrecord" + (_CODECS[codec][0] if codec else "")
 
         return _Factory()
 
@@ -268,7 +366,8 @@ class DefaultSource:
 
     def save(self, path: str, schema: StructType, rows: Sequence[Sequence], options: Optional[Dict[str, str]] = None) -> None:
         os.makedirs(path, exist_ok=True)
-        w = self.prepareWrite(options or {}, schema).newInstance(os.path.join(path, "part-00000.tfrecord"), schema)
+        factory = self.prepareWrite(options or {}, schema)
+        w = factory.newInstance(os.path.join(path, "part-00000" + factory.getFileExtension()), schema)
         for r in rows:
             w.write(r)
         w.close()

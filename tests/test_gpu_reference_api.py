@@ -282,3 +282,35 @@ def test_java_utf8_replacement_on_gpu(io, oracle):
     assert batch.info["error_code"] == 0
     assert_columns_equal(batch.to_host(), want.columns, sch.names, "java utf8")
     batch.release(); dec.close()
+
+
+@pytest.mark.parametrize("codec,ext", [("org.apache.hadoop.io.compress.GzipCodec", ".gz"), ("org.apache.hadoop.io.compress.DefaultCodec", ".deflate"),
+                                       ("org.apache.hadoop.io.compress.BZip2Codec", ".bz2"), ("gzip", ".gz")])
+def test_io_codec_option_and_read_by_extension(io, oracle, tmp_path, codec, ext):
+    """M/DefaultSource.scala:94-102,110-112 (write: `codec` option -> compressed stream, extension from the codec) and
+    Hadoop's read-side codec choice by file extension; the compressed container holds exactly the writer's framed bytes."""
+    import bz2, gzip, zlib
+    path = str(tmp_path / "out")
+    src = io.DefaultSource()
+    src.save(path, exampleSchema, exampleTestRows, {"recordType": "Example", "codec": codec})
+    part = path + "/part-00000.tfrecord" + ext
+    raw = open(part, "rb").read()
+    framed = {".gz": gzip.decompress, ".deflate": zlib.decompress, ".bz2": bz2.decompress}[ext](raw)
+    plain = str(tmp_path / "plain")
+    src.save(plain, exampleSchema, exampleTestRows, {"recordType": "Example"})
+    assert framed == open(plain + "/part-00000.tfrecord", "rb").read()
+    got = sorted(src.load(path, exampleSchema, {"recordType": "Example"}), key=lambda r: r[6])
+    assert len(got) == 3
+    for g, w in zip(got, exampleTestRows):
+        assert _approx(list(g), list(w)), (g, w)
+    # blocks smaller than the file: the decompressed stream is carried across decode calls like a plain file
+    rows = list(io.TFRecordFileReader.readFile(None, {"recordType": "Example"}, io.PartitionedFile(part), exampleSchema, block_bytes=300))
+    assert len(rows) == 3
+    # schema inference reads through the same codec
+    names = set(src.inferSchema({"recordType": "Example"}, [part]).names)
+    assert names == set(exampleSchema.names)
+
+
+def test_io_unknown_codec_is_rejected(io, tmp_path):
+    with pytest.raises(io.native.IllegalArgumentException):
+        io.DefaultSource().save(str(tmp_path / "x"), exampleSchema, exampleTestRows, {"codec": "org.apache.hadoop.io.compress.SnappyCodec"})

@@ -147,3 +147,23 @@ def test_bench_reference_arm_runs_on_cpu():
     line = json.loads(p.stdout.strip().splitlines()[-1])
     assert line["impl"] == "reference" and line["unit"] == "GB/s" and line["value"] > 0
     assert line["cpu_baseline"]["kind"] == "port" and line["e2e"]["h2d_bytes_per_step"] == 0
+
+
+def test_codec_names_and_extensions():
+    """M/DefaultSource.scala:94-102,110-112: the `codec` option names a Hadoop codec class; the extension follows it"""
+    from spark_tfrecord_b200 import io, _native
+    assert io._codec_name("") is None
+    assert io._codec_name("org.apache.hadoop.io.compress.GzipCodec") == "gzip" and io._CODECS["gzip"][0] == ".gz"
+    assert io._codec_name("org.apache.hadoop.io.compress.DefaultCodec") == "deflate" and io._CODECS["deflate"][0] == ".deflate"
+    assert io._codec_name("BZip2Codec") == "bzip2" and io._codec_of_path("p/part-0.tfrecord.bz2") == "bzip2"
+    assert io._codec_of_path("p/part-0.tfrecord") is None
+    with pytest.raises(_native.IllegalArgumentException):
+        io._codec_name("org.apache.hadoop.io.compress.SnappyCodec")
+    import os, tempfile, zlib
+    d = tempfile.mkdtemp()
+    for name, (ext, _) in io._CODECS.items():
+        p = os.path.join(d, "f.tfrecord" + ext)
+        w = io._open_write(p, name); w.write(b"abc" * 70000); w.write(b"tail"); w.close()
+        with io._open_read(p) as f:
+            assert f.read(5) == b"abcab" and f.read() == (b"abc" * 70000 + b"tail")[5:]
+    assert zlib.decompress(open(os.path.join(d, "f.tfrecord.deflate"), "rb").read()) == b"abc" * 70000 + b"tail"
