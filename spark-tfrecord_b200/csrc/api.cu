@@ -645,8 +645,15 @@ static int32_t finish_var_and_views(DecodeCtx& C, DecodeArgs& A, uint32_t n_eff,
       uint32_t g2 = (uint32_t)std::min<unsigned long long>((cells + 255) / 256, (unsigned long long)d->ctx->sm_count * 16);
       g2 = std::max<uint32_t>(g2, 1);
       d->span_begin(3);
+      int nl2 = 1;
+      if (A.flist_warp) {      // canonical FeatureList cells with fixed-width elements: one warp per cell
+        const unsigned long long wcells = (unsigned long long)n_eff * S.n_var;
+        const uint32_t gw = (uint32_t)std::min<unsigned long long>((wcells + warps - 1) / warps, (unsigned long long)d->ctx->sm_count * 32);
+        decode_pass2_flist_kernel<<<std::max<uint32_t>(gw, 1), warps * 32, 0, st>>>(A);
+        ++nl2;
+      }
       decode_pass2_kernel<<<g2, warps * 32, 0, st>>>(A);
-      d->span_end(1);
+      d->span_end(nl2);
     }
   } else {
     // uniform mode: the var block was allocated up front, one level per column
@@ -868,6 +875,7 @@ static int32_t decode_impl(tfr_decoder* d, const void* data, size_t nbytes, int3
         if (!(tflags & TF_FALLBACK)) {
           if (d->h_stats->overflow)
             for (int a = 0; a < S.n_cnt; ++a) if (totals[a] < 0 || totals[a] > 0x7fffffffLL) return fail(TFR_E_BATCH_TOO_LARGE, "Arrow int32 offsets overflow; decode smaller blocks");
+          A.flist_warp = S.record_type == TFR_RT_SEQUENCE_EXAMPLE && !getenv("TFR_DISABLE_FLIST_WARP");   // the tile kernel validated every FeatureList as canonical
           TRY(finish_var_and_views(C, A, n, totals, true, false));
           done = true;
           // learn shapes: every variable-width column single-level and total == n * (count of row 0)

@@ -125,6 +125,16 @@ __device__ __forceinline__ uint32_t crc_warp(const uint32_t* stab, const uint8_t
 }
 
 // ---------------------------------------------------------------------------------------------
+// warp-wide exclusive prefix sum over the lanes (+ the total)
+__device__ __forceinline__ uint32_t warp_excl_scan_u32(uint32_t v, uint32_t& total) {
+  const uint32_t lane = threadIdx.x & 31;
+  uint32_t x = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= (uint32_t)o) x += y; }
+  total = __shfl_sync(0xffffffffu, x, 31);
+  return x - v;
+}
+
 // protobuf wire primitives (protobuf-java CodedInputStream semantics, see oracle/tfr_oracle.c)
 // ---------------------------------------------------------------------------------------------
 struct Cur {
