@@ -652,6 +652,12 @@ static int32_t finish_var_and_views(DecodeCtx& C, DecodeArgs& A, uint32_t n_eff,
         decode_pass2_flist_kernel<<<std::max<uint32_t>(gw, 1), warps * 32, 0, st>>>(A);
         ++nl2;
       }
+      if (S.record_type != TFR_RT_BYTE_ARRAY && !getenv("TFR_DISABLE_CANON_LEAN")) {   // the ordinary cells: small kernel, many resident threads
+        A.canon_lean = 1;
+        const uint32_t gl = (uint32_t)std::min<unsigned long long>((cells + 255) / 256, (unsigned long long)d->ctx->sm_count * 48);
+        decode_pass2_canon_kernel<<<std::max<uint32_t>(gl, 1), 256, 0, st>>>(A);
+        ++nl2;
+      }
       decode_pass2_kernel<<<g2, warps * 32, 0, st>>>(A);
       d->span_end(nl2);
     }

@@ -45,6 +45,7 @@ struct DecodeArgs {
   void* const* var_values;    // [n_var] leaf value buffers
   const int32_t* var_field;   // [n_var] schema field of each var slot
   uint32_t flist_warp;        // 1: canonical FeatureList cells with fixed-width elements are emitted by decode_pass2_flist_kernel
+  uint32_t canon_lean;        // 1: scalar string/binary cells and canonical 1-D list cells are emitted by decode_pass2_canon_kernel
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -479,11 +480,39 @@ __device__ __forceinline__ void sink_float(ElemSink& s, uint32_t bits) {
   else reinterpret_cast<double*>(s.values)[s.vpos] = (double)__uint_as_float(bits);
   s.vpos++; s.taken++;
 }
+// copy l bytes (any alignment on both sides), 16 at a time: the bytes are loaded as words before they are stored (a plain
+// byte loop is one dependent global load -> store chain: the compiler cannot move a load above the previous store of the
+// other pointer).  Only words that hold a needed byte (plus the one word after, which is still inside the record: every
+// payload is followed by its 4-byte CRC) are read.  With ascii_only, the copy stops BEFORE the first 16-byte group that
+// holds a byte >= 0x80 and returns false (nothing past the ASCII prefix has been written).
+__device__ __forceinline__ bool copy_bytes16(uint8_t* d, const uint8_t* p, uint32_t l, bool ascii_only) {
+  for (uint32_t i = 0; i < l; i += 16) {
+    const uint32_t r = min(16u, l - i);
+    uint32_t w[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) w[k] = (uint32_t)(4 * k) < r ? load_u32_unaligned(p + i + 4 * k) : 0u;
+    if (ascii_only) {
+      uint32_t hi = 0;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const uint32_t live = r >= (uint32_t)(4 * k + 4) ? 0xffffffffu : r > (uint32_t)(4 * k) ? (1u << (8 * (r - 4 * k))) - 1u : 0u;   // bytes of word k below l
+        hi |= w[k] & live;
+      }
+      if (hi & 0x80808080u) return false;
+    }
+#pragma unroll
+    for (int k = 0; k < 16; ++k)
+      if ((uint32_t)k < r) d[i + k] = (uint8_t)(w[k >> 2] >> (8 * (k & 3)));
+  }
+  return true;
+}
 __device__ __forceinline__ void sink_bytes(ElemSink& s, const uint8_t* p, uint32_t l) {
   if (s.taken >= s.limit) return;
   uint8_t* d = s.values + s.vpos;
-  if (s.elem_type == TFR_T_STRING && !all_ascii(p, l)) s.vpos += java_utf8_transcode(p, l, d);
-  else { for (uint32_t i = 0; i < l; ++i) d[i] = p[i]; s.vpos += l; }
+  // StringType = Java UTF-8 decode + re-encode: the identity for ASCII; anything else goes through the transcoder, which
+  // rewrites the cell from its start (the ASCII prefix already copied is what it writes there too)
+  if (copy_bytes16(d, p, l, s.elem_type == TFR_T_STRING)) s.vpos += l;
+  else s.vpos += java_utf8_transcode(p, l, d);
   if (s.leaf_off) { s.leaf_off[s.epos + 1] = (int32_t)s.vpos; s.epos++; }
   s.taken++;
 }
@@ -556,6 +585,62 @@ __device__ __forceinline__ void step_feature_emit(Cur body, ElemSink& s) {
   feature_occ_walk(body, o, 1, &s);
 }
 
+// the rare string that is not ASCII: kept out of line so that the lean kernel below stays small
+__device__ __noinline__ uint32_t transcode_cell(const uint8_t* p, uint32_t l, uint8_t* d) { return java_utf8_transcode(p, l, d); }
+
+// pass 2 for the cells every ordinary file consists of: scalar string / binary columns (the first element of a BytesList)
+// and canonical 1-D lists (one packed field, or a plain BytesList).  Same thread-per-(row, cell) mapping as
+// decode_pass2_kernel, but without the general two-walk emitter inlined: 32 registers instead of 128 + stack, four times
+// the resident threads, and every cell is a chain of dependent loads, so the time goes with the resident threads.
+__global__ void __launch_bounds__(256, 6) decode_pass2_canon_kernel(DecodeArgs A) {
+  const uint32_t nvar = (uint32_t)A.sch.n_var;
+  const unsigned long long total = (unsigned long long)A.n_eff * nvar;
+  for (unsigned long long cidx = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; cidx < total; cidx += (unsigned long long)gridDim.x * blockDim.x) {
+    const uint32_t row = (uint32_t)(cidx / nvar), v = (uint32_t)(cidx % nvar);
+    const DevField& fd = A.sch.fields[A.var_field[v]];
+    if (fd.depth > 1) continue;
+    const int32_t* sc = A.scan[fd.cnt_slot];
+    const int32_t off0 = sc[row];
+    const uint32_t cnt0 = (uint32_t)(sc[row + 1] - off0);
+    if (cnt0 == 0) continue;                                  // null, empty list or empty string
+    if (fd.depth == 1 && A.cflag[(size_t)v * A.n + row] != CF_CANON) continue;
+    const uint8_t* p = A.data + A.src[(size_t)v * A.n + row];
+    uint8_t* values = reinterpret_cast<uint8_t*>(A.var_values[v]);
+    const bool is_str = fd.elem_type == TFR_T_STRING;
+    if (fd.depth == 0) {                                      // src = the length varint of the first element
+      Cur c{p, p + 16};
+      uint32_t l = 0; uint64_t lv;
+      if (rd_varint64(c, lv)) l = (uint32_t)lv;
+      uint8_t* d = values + (uint32_t)off0;
+      if (!copy_bytes16(d, c.p, l, is_str)) transcode_cell(c.p, l, d);
+      continue;
+    }
+    if (fd.kind == K_FLOAT) {                                 // src = the packed payload
+      if (fd.elem_type == TFR_T_FLOAT32) { uint32_t* d = reinterpret_cast<uint32_t*>(values) + off0; for (uint32_t i = 0; i < cnt0; ++i) d[i] = load_u32_unaligned(p + 4 * i); }
+      else { double* d = reinterpret_cast<double*>(values) + off0; for (uint32_t i = 0; i < cnt0; ++i) d[i] = (double)__uint_as_float(load_u32_unaligned(p + 4 * i)); }
+    } else if (fd.kind == K_INT64) {
+      Cur pk{p, p + (size_t)cnt0 * 10};
+      for (uint32_t i = 0; i < cnt0; ++i) {
+        uint64_t x; if (!rd_varint64(pk, x)) break;
+        if (fd.elem_type == TFR_T_INT64) reinterpret_cast<int64_t*>(values)[(uint32_t)off0 + i] = (int64_t)x;
+        else reinterpret_cast<int32_t*>(values)[(uint32_t)off0 + i] = (int32_t)(uint32_t)x;
+      }
+    } else {                                                  // src = the BytesList body: { 0A blen bytes }*
+      int32_t* leaf = A.offs[v * 3 + 1];
+      uint32_t vpos = (uint32_t)A.scan[fd.cnt_slot + 1][row];
+      Cur c{p, A.data + A.nbytes};
+      for (uint32_t i = 0; i < cnt0; ++i) {
+        uint32_t tag, l;
+        if (!rd_tag(c, tag) || !rd_len(c, l)) break;
+        uint8_t* d = values + vpos;
+        if (copy_bytes16(d, c.p, l, is_str)) vpos += l; else vpos += transcode_cell(c.p, l, d);
+        leaf[(uint32_t)off0 + i + 1] = (int32_t)vpos;
+        c.p += l;
+      }
+    }
+  }
+}
+
 __global__ void __launch_bounds__(256) decode_pass2_kernel(DecodeArgs A) {
   const uint32_t warps = blockDim.x >> 5, wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t nvar = (uint32_t)A.sch.n_var;
@@ -588,6 +673,7 @@ __global__ void __launch_bounds__(256) decode_pass2_kernel(DecodeArgs A) {
       s.elem_type = fd.elem_type; s.values = reinterpret_cast<uint8_t*>(A.var_values[v]);
       s.leaf_off = nullptr; s.epos = 0; s.limit = 0xffffffffu; s.taken = 0;
       const bool varlen = fd.elem_type == TFR_T_STRING || fd.elem_type == TFR_T_BINARY;
+      if (A.canon_lean && (fd.depth == 0 || (fd.depth == 1 && flag == CF_CANON))) continue;   // decode_pass2_canon_kernel
       if (fd.depth == 0) {                                   // scalar string / binary
         Cur c{A.data + src, A.data + src + 16};              // length varint of the first element (validated in pass 1)
         uint32_t l = 0; uint64_t lv;
