@@ -243,23 +243,12 @@ __global__ void __launch_bounds__(TILE_THREADS, TILE_MIN_CTAS) decode_tile_kerne
     }
     const uint32_t total = __reduce_add_sync(FULLMASK, cbytes);
     if (lane == 0) {
-#if defined(TILE_CONSTS_LDG)
-      mbar_expect_tx(bar, total);
-#else
       mbar_expect_tx(bar, total + A.const_bytes);
       bulk_g2s(smem_raw + 16, A.consts, A.const_bytes, bar);      // CRC tables, zeroed seen words, schema, templates, names
-#endif
     }
     __syncwarp();
     if (cbytes) bulk_g2s(tile_b + lane * A.slot, A.data + (off - head), cbytes, bar);
   }
-#if defined(TILE_CONSTS_LDG)
-  {
-    const uint4* g = reinterpret_cast<const uint4*>(A.consts);
-    uint4* sd = reinterpret_cast<uint4*>(smem_raw + 16);
-    for (uint32_t i = threadIdx.x; i < A.const_bytes / 16; i += TILE_THREADS) sd[i] = __ldg(g + i);
-  }
-#endif
   __syncthreads();                                                // the barrier is initialised before anyone waits on it
   mbar_wait(bar, 0);
 

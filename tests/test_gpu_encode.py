@@ -213,3 +213,62 @@ def test_tile_emit_shapes(native, oracle):
         finally:
             del os.environ["TFR_DISABLE_FAST"]
         assert got2 == want, _diff(got2, want)
+
+
+def test_one_kernel_encoder_after_the_first_call(native, oracle, monkeypatch):
+    """With TFR_FUSED_ENCODE=1 the second and later calls of an encoder take the one-kernel path (sizes + look-back offsets
+    + emit), with the slot size learned from the previous call: same bytes; a batch with a much larger row falls back and
+    re-learns; a null in a non-nullable column is reported at the same row."""
+    monkeypatch.setenv("TFR_FUSED_ENCODE", "1")
+    from oracle.corpus import cfg2_columns, mixed_columns
+    rng = np.random.default_rng(9)
+    sch, cols = cfg2_columns(3000, seed=77)
+    want, rc, _ = oracle.encode(cols, sch)
+    enc = native.Encoder(sch, 0)
+    try:
+        for _ in range(3):                                         # 1: two passes (learn), 2-3: one kernel
+            assert enc.encode(cols) == want
+        sch2, cols2 = cfg2_columns(1, seed=78)                     # a single row: one partial tile
+        want2, _, _ = oracle.encode(cols2, sch2)
+        assert enc.encode(cols2) == want2
+        sch3, cols3 = cfg2_columns(4097, seed=79, small_ints=True) # other varint widths, 129 tiles
+        want3, _, _ = oracle.encode(cols3, sch3)
+        assert enc.encode(cols3) == want3
+    finally:
+        enc.close()
+    # ragged rows, nulls, strings; then one row far larger than anything seen before (slot overflow -> fallback -> re-learn)
+    schm = StructType([StructField("a", LongType()), StructField("s", StringType()), StructField("v", ArrayType(LongType())),
+                       StructField("f", ArrayType(FloatType())), StructField("b", ArrayType(BinaryType()))])
+    def rows(n, big=None):
+        out = []
+        for i in range(n):
+            out.append((None if i % 7 == 3 else int(rng.integers(-2**62, 2**62)), None if i % 5 == 1 else "s" * (i % 40),
+                        [int(x) for x in rng.integers(-1000, 1000, i % 6)], [float(x) for x in rng.standard_normal(i % 4).astype(np.float32)],
+                        [bytes(rng.integers(0, 256, (i + k) % 9, dtype=np.uint8)) for k in range(i % 3)]))
+        if big is not None:
+            out[big] = (5, "y" * 3000, list(range(500)), [1.5] * 700, [b"z" * 900])
+        return out
+    enc = native.Encoder(schm, 0)
+    try:
+        for data in (rows(500), rows(500), rows(777, big=300), rows(777, big=5), rows(64)):
+            c = A.columns_from_rows(schm, data)
+            w, rc, _ = oracle.encode(c, schm)
+            assert rc == 0
+            g = enc.encode(c)
+            assert g == w, _diff(g, w)
+    finally:
+        enc.close()
+    # NullPointerException on the one-kernel path
+    schn = StructType([StructField("ok", LongType()), StructField("NonNullLabel", ArrayType(FloatType()), nullable=False)])
+    good = A.columns_from_rows(schn, [(i, [1.0 * i]) for i in range(100)])
+    bad = A.columns_from_rows(schn, [(i, None if i in (41, 77) else [1.0 * i]) for i in range(100)])
+    enc = native.Encoder(schn, 0)
+    try:
+        w, _, _ = oracle.encode(good, schn)
+        assert enc.encode(good) == w and enc.encode(good) == w
+        with pytest.raises(native.NullPointerException) as ei:
+            enc.encode(bad)
+        assert ei.value.row == 41
+        assert enc.encode(good) == w
+    finally:
+        enc.close()
