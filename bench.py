@@ -18,6 +18,10 @@ CRC verified).  Prints ONE JSON line (rank 0).
            recorded by the library around every launch in the timed region), against the measured HBM copy
            bandwidth in MEASURED_PEAKS.json.
   cpu_baseline: the oracle port (C restatement of the reference's per-record algorithm) on the host cores.
+
+The synthetic columns are seeded numpy data; our arm frames them with the product's GPU encoder (proved byte-identical
+to the reference writer by tests/test_gpu_encode.py), the CPU arm with the oracle's writer.  Nothing under oracle/ is
+executed outside the cpu_baseline leg and the --impl reference arm.
 """
 from __future__ import annotations
 
@@ -61,19 +65,63 @@ def dist_env():
 
 
 # ---------------------------------------------------------------------------------------------
-# corpus: configs[1] records, encoded by the CPU oracle's writer (independent of the CUDA encoder)
+# corpus: configs[1] records.  The columns are seeded numpy data; our arm frames them with the product's own GPU encoder
+# (tests/test_gpu_encode.py proves its bytes identical to the reference writer's), the CPU arm with the oracle's writer:
+# the oracle is executed only by the CPU legs of this file.
 # ---------------------------------------------------------------------------------------------
-def make_batches(batch_mib: int, pool: int, seed: int):
-    from oracle import corpus, oracle
+def cfg2_schema_and_columns(n: int, seed: int):
+    """32 x Int64List[1], 16 x FloatList[8], 16 x BytesList[1] (16 B), entries in schema order (same generator and seeds as
+    the parity tests' corpus)"""
+    from spark_tfrecord_b200._cabi import HostColumn
+    from spark_tfrecord_b200.sqltypes import (ArrayType, BinaryType, FloatType, LongType, StructField, StructType, TFR_T_BINARY, TFR_T_FLOAT32,
+                                              TFR_T_INT64)
+    rng = np.random.Generator(np.random.PCG64(seed))
+    valid = np.full((n + 7) // 8, 0xFF, dtype=np.uint8)
+    if n % 8 and len(valid):
+        valid[-1] = (1 << (n % 8)) - 1
+    fields = [StructField(f"i{i:02d}", LongType()) for i in range(32)]
+    fields += [StructField(f"f{i:02d}", ArrayType(FloatType())) for i in range(16)]
+    fields += [StructField(f"b{i:02d}", BinaryType()) for i in range(16)]
+    cols = []
+    for i in range(32):
+        v = rng.integers(0, 2**21, n, dtype=np.int64)
+        if i % 8 == 7:          # quarter each of [0,127], [128,2^31), [-2^31,0), full int64
+            sel = rng.integers(0, 4, n)
+            a = rng.integers(0, 128, n, dtype=np.int64)
+            b = rng.integers(128, 2**31, n, dtype=np.int64)
+            c = rng.integers(-2**31, 0, n, dtype=np.int64)
+            d = rng.integers(-2**63, 2**63 - 1, n, dtype=np.int64, endpoint=True)
+            v = np.choose(sel, [a, b, c, d])
+        cols.append(HostColumn(TFR_T_INT64, 0, n, valid, [], v))
+    for i in range(16):
+        vals = rng.standard_normal(n * 8, dtype=np.float32)
+        cols.append(HostColumn(TFR_T_FLOAT32, 1, n, valid, [(np.arange(n + 1, dtype=np.int64) * 8).astype(np.int32)], vals))
+    for i in range(16):
+        data = rng.integers(0, 256, n * 16, dtype=np.uint8)
+        cols.append(HostColumn(TFR_T_BINARY, 0, n, valid, [(np.arange(n + 1, dtype=np.int64) * 16).astype(np.int32)], data))
+    return StructType(fields), cols
+
+
+def make_batches(batch_mib: int, pool: int, seed: int, device=None):
+    """device = a CUDA device index: framed by the product's encoder on that GPU; None: by the oracle's writer (CPU arm)"""
     rec_bytes = 1728                      # measured mean framed record size of this schema (printed below)
     n = max(1, (batch_mib << 20) // rec_bytes)
-    schema = corpus.cfg2_schema()
     out = []
+    enc = None
+    schema = None
     for i in range(pool):
-        _, cols = corpus.cfg2_columns(n, seed=seed + 1000 * i)
-        data, rc, _ = oracle.encode(cols, schema)
-        assert rc == 0
+        schema, cols = cfg2_schema_and_columns(n, seed=seed + 1000 * i)
+        if device is None:
+            from oracle import oracle
+            data, rc, _ = oracle.encode(cols, schema)
+            assert rc == 0
+        else:
+            from spark_tfrecord_b200 import _native
+            enc = enc or _native.Encoder(schema, 0, device)
+            data = enc.encode(cols)
         out.append(np.frombuffer(data, dtype=np.uint8))
+    if enc is not None:
+        enc.close()
     return schema, n, out
 
 
@@ -322,7 +370,7 @@ def run_ours(args):
     while avail is not None and batch_mib > 128 and 8 * 10 * (batch_mib << 20) > avail:
         batch_mib //= 2
         reduced = True
-    schema, n_rec, batches = make_batches(batch_mib, args.pool, seed=2024 + 7919 * rank)
+    schema, n_rec, batches = make_batches(batch_mib, args.pool, seed=2024 + 7919 * rank, device=dev)
     batch_bytes = [int(b.nbytes) for b in batches]
     d_batches = [torch.from_numpy(b.copy()).cuda(dev) for b in batches]
 

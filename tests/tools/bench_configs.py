@@ -2,8 +2,8 @@
 Resident timing (inputs in HBM), wall clock around synchronous C-ABI calls, best of 5 after 2 warm-ups.
 Every result is parity-checked against the oracle on the same data before it is timed."""
 import json, os, sys, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
 import numpy as np, torch
 from oracle import oracle, corpus
 from spark_tfrecord_b200 import _native, _cabi as A

@@ -2,7 +2,7 @@
 pruning), schema order different from the file's entry order, small records.  Each result is checked against the
 oracle on the same bytes first.  Wall clock around synchronous C-ABI calls, best of 5 after 2 warm-ups."""
 import json, os, sys, time
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import numpy as np, torch
 from oracle import oracle, corpus

@@ -1,6 +1,6 @@
 """scratch timing of the resident decode path (not the contract bench)"""
 import sys, os, time
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np, torch
 from oracle import oracle, corpus
 from spark_tfrecord_b200 import _native
