@@ -407,7 +407,7 @@ def run_ours(args):
     # ---------------- end to end: pinned host -> device -> pinned host ----------------
     e2e = None
     if not args.no_e2e:
-        n_workers = 3
+        n_workers = int(os.environ.get("TFR_E2E_WORKERS", "3"))
         decs = [_native.Decoder(schema, 0, dev) for _ in range(n_workers)]
         stages = []
         for w, d in enumerate(decs):
@@ -519,7 +519,7 @@ def run_ours(args):
     }
     if e2e:
         line["e2e"] = {"value": tot_e2e / t_e2e_max / 1e9, "unit": UNIT, "h2d_bytes_per_step": int(batch_bytes[0]),
-                       "d2h_bytes_per_step": int(e2e[2]), "pipeline": "3 decoder handles (threads), pinned staging in, pinned Arrow buffers out"}
+                       "d2h_bytes_per_step": int(e2e[2]), "pipeline": f"{n_workers} decoder handles (threads), pinned staging in, pinned Arrow buffers out"}
     # ---------------- CPU baseline beside it (rank 0, N=1 only) ----------------
     if not args.no_cpu and world == 1:
         cores = host_cores()
