@@ -654,7 +654,8 @@ static int32_t finish_var_and_views(DecodeCtx& C, DecodeArgs& A, uint32_t n_eff,
       }
       if (S.record_type != TFR_RT_BYTE_ARRAY && !getenv("TFR_DISABLE_CANON_LEAN")) {   // the ordinary cells: small kernel, many resident threads
         A.canon_lean = 1;
-        const uint32_t gl = (uint32_t)std::min<unsigned long long>((cells + 255) / 256, (unsigned long long)d->ctx->sm_count * 48);
+        const unsigned long long wgroups = (unsigned long long)((n_eff + 31) / 32) * S.n_var;      // one warp per (32 rows, column)
+        const uint32_t gl = (uint32_t)std::min<unsigned long long>((wgroups + 7) / 8, (unsigned long long)d->ctx->sm_count * 48);
         decode_pass2_canon_kernel<<<std::max<uint32_t>(gl, 1), 256, 0, st>>>(A);
         ++nl2;
       }

@@ -592,52 +592,100 @@ __device__ __noinline__ uint32_t transcode_cell(const uint8_t* p, uint32_t l, ui
 // and canonical 1-D lists (one packed field, or a plain BytesList).  Same thread-per-(row, cell) mapping as
 // decode_pass2_kernel, but without the general two-walk emitter inlined: 32 registers instead of 128 + stack, four times
 // the resident threads, and every cell is a chain of dependent loads, so the time goes with the resident threads.
+#define CANON_STAGE_BYTES 2048
 __global__ void __launch_bounds__(256, 6) decode_pass2_canon_kernel(DecodeArgs A) {
+  // One warp takes 32 consecutive rows of ONE variable-width column (lane = row): the cells of those rows are adjacent in
+  // the output, so the warp assembles them in shared memory and writes the range with coalesced word stores; a thread
+  // per cell writing its own bytes costs one 32-byte sector per byte stored.
+  __shared__ __align__(16) uint8_t s_stage[8][CANON_STAGE_BYTES + 16];
+  const uint32_t warps = blockDim.x >> 5, wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t nvar = (uint32_t)A.sch.n_var;
-  const unsigned long long total = (unsigned long long)A.n_eff * nvar;
-  for (unsigned long long cidx = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; cidx < total; cidx += (unsigned long long)gridDim.x * blockDim.x) {
-    const uint32_t row = (uint32_t)(cidx / nvar), v = (uint32_t)(cidx % nvar);
+  const uint32_t groups = (A.n_eff + 31) / 32;
+  const unsigned long long total = (unsigned long long)groups * nvar;
+  for (unsigned long long gidx = (unsigned long long)blockIdx.x * warps + wid; gidx < total; gidx += (unsigned long long)gridDim.x * warps) {
+    const uint32_t v = (uint32_t)(gidx % nvar), row = (uint32_t)(gidx / nvar) * 32 + lane;
     const DevField& fd = A.sch.fields[A.var_field[v]];
-    if (fd.depth > 1) continue;
+    if (fd.depth > 1) continue;                                           // warp-uniform
+    const bool in = row < A.n_eff;
     const int32_t* sc = A.scan[fd.cnt_slot];
-    const int32_t off0 = sc[row];
-    const uint32_t cnt0 = (uint32_t)(sc[row + 1] - off0);
-    if (cnt0 == 0) continue;                                  // null, empty list or empty string
-    if (fd.depth == 1 && A.cflag[(size_t)v * A.n + row] != CF_CANON) continue;
-    const uint8_t* p = A.data + A.src[(size_t)v * A.n + row];
+    const int32_t off0 = in ? sc[row] : 0;
+    uint32_t cnt0 = in ? (uint32_t)(sc[row + 1] - off0) : 0u;             // elements, or bytes of a scalar string
+    bool foreign = false;                                                 // a non-empty cell that decode_pass2_kernel writes
+    if (cnt0 && fd.depth == 1 && A.cflag[(size_t)v * A.n + row] != CF_CANON) { cnt0 = 0; foreign = true; }
+    const uint8_t* p = A.data + (cnt0 ? A.src[(size_t)v * A.n + row] : 0u);
     uint8_t* values = reinterpret_cast<uint8_t*>(A.var_values[v]);
     const bool is_str = fd.elem_type == TFR_T_STRING;
-    if (fd.depth == 0) {                                      // src = the length varint of the first element
-      Cur c{p, p + 16};
-      uint32_t l = 0; uint64_t lv;
-      if (rd_varint64(c, lv)) l = (uint32_t)lv;
-      uint8_t* d = values + (uint32_t)off0;
-      if (!copy_bytes16(d, c.p, l, is_str)) transcode_cell(c.p, l, d);
+    const bool bytes_leaf = fd.kind == K_BYTES;
+    if (fd.depth == 1 && bytes_leaf) {                                    // list of strings: element loop per lane, direct stores
+      if (cnt0) {
+        int32_t* leaf = A.offs[v * 3 + 1];
+        uint32_t vpos = (uint32_t)A.scan[fd.cnt_slot + 1][row];
+        Cur c{p, A.data + A.nbytes};
+        for (uint32_t i = 0; i < cnt0; ++i) {
+          uint32_t tag, l;
+          if (!rd_tag(c, tag) || !rd_len(c, l)) break;
+          uint8_t* d = values + vpos;
+          if (copy_bytes16(d, c.p, l, is_str)) vpos += l; else vpos += transcode_cell(c.p, l, d);
+          leaf[(uint32_t)off0 + i + 1] = (int32_t)vpos;
+          c.p += l;
+        }
+      }
       continue;
     }
-    if (fd.kind == K_FLOAT) {                                 // src = the packed payload
-      if (fd.elem_type == TFR_T_FLOAT32) { uint32_t* d = reinterpret_cast<uint32_t*>(values) + off0; for (uint32_t i = 0; i < cnt0; ++i) d[i] = load_u32_unaligned(p + 4 * i); }
-      else { double* d = reinterpret_cast<double*>(values) + off0; for (uint32_t i = 0; i < cnt0; ++i) d[i] = (double)__uint_as_float(load_u32_unaligned(p + 4 * i)); }
-    } else if (fd.kind == K_INT64) {
-      Cur pk{p, p + (size_t)cnt0 * 10};
-      for (uint32_t i = 0; i < cnt0; ++i) {
-        uint64_t x; if (!rd_varint64(pk, x)) break;
-        if (fd.elem_type == TFR_T_INT64) reinterpret_cast<int64_t*>(values)[(uint32_t)off0 + i] = (int64_t)x;
-        else reinterpret_cast<int32_t*>(values)[(uint32_t)off0 + i] = (int32_t)(uint32_t)x;
-      }
-    } else {                                                  // src = the BytesList body: { 0A blen bytes }*
-      int32_t* leaf = A.offs[v * 3 + 1];
-      uint32_t vpos = (uint32_t)A.scan[fd.cnt_slot + 1][row];
-      Cur c{p, A.data + A.nbytes};
-      for (uint32_t i = 0; i < cnt0; ++i) {
-        uint32_t tag, l;
-        if (!rd_tag(c, tag) || !rd_len(c, l)) break;
-        uint8_t* d = values + vpos;
-        if (copy_bytes16(d, c.p, l, is_str)) vpos += l; else vpos += transcode_cell(c.p, l, d);
-        leaf[(uint32_t)off0 + i + 1] = (int32_t)vpos;
-        c.p += l;
+    // output bytes of this lane's cell and of the whole group (adjacent rows -> adjacent output)
+    const uint32_t w = bytes_leaf ? 1u : (uint32_t)fd.width;
+    const uint32_t my_bytes = cnt0 * w;
+    uint32_t grp_bytes;
+    const uint32_t my_off = warp_excl_scan_u32(my_bytes, grp_bytes);
+    if (grp_bytes == 0) continue;
+    // first output byte of the group: the first lane that has a cell knows it
+    const uint32_t has = __ballot_sync(0xffffffffu, cnt0 != 0);
+    const uint32_t first_lane = (uint32_t)__ffs((int)has) - 1;
+    const unsigned long long base = __shfl_sync(0xffffffffu, (unsigned long long)(uint32_t)off0 * w, first_lane);
+    // staging needs the group's cells to be one contiguous output range: no cell of another kernel in between
+    const bool staged = grp_bytes <= CANON_STAGE_BYTES && !__any_sync(0xffffffffu, foreign);
+    uint8_t* d = staged ? s_stage[wid] + (uint32_t)(base & 3) + my_off : values + (size_t)(uint32_t)off0 * w;
+    bool redo = false;                                                    // a non-ASCII string: the transcoder writes it
+    if (cnt0) {
+      if (fd.depth == 0) {                                                // src = the length varint of the first element
+        Cur c{p, p + 16};
+        uint32_t l = 0; uint64_t lv;
+        if (rd_varint64(c, lv)) l = (uint32_t)lv;
+        p = c.p;
+        if (!copy_bytes16(d, p, l, is_str)) { redo = true; if (!staged) transcode_cell(p, l, d); }
+        cnt0 = l;
+      } else if (fd.kind == K_FLOAT) {                                    // src = the packed payload
+        if (fd.elem_type == TFR_T_FLOAT32) { uint32_t* q = reinterpret_cast<uint32_t*>(d); for (uint32_t i = 0; i < cnt0; ++i) { const uint32_t x = load_u32_unaligned(p + 4 * i); if (staged) memcpy(d + 4 * i, &x, 4); else q[i] = x; } }
+        else { for (uint32_t i = 0; i < cnt0; ++i) { const double x = (double)__uint_as_float(load_u32_unaligned(p + 4 * i)); if (staged) memcpy(d + 8 * i, &x, 8); else reinterpret_cast<double*>(d)[i] = x; } }
+      } else {
+        Cur pk{p, p + (size_t)cnt0 * 10};
+        for (uint32_t i = 0; i < cnt0; ++i) {
+          uint64_t x; if (!rd_varint64(pk, x)) break;
+          if (fd.elem_type == TFR_T_INT64) { const int64_t y = (int64_t)x; if (staged) memcpy(d + 8 * i, &y, 8); else reinterpret_cast<int64_t*>(d)[i] = y; }
+          else { const int32_t y = (int32_t)(uint32_t)x; if (staged) memcpy(d + 4 * i, &y, 4); else reinterpret_cast<int32_t*>(d)[i] = y; }
+        }
       }
     }
+    if (!staged) continue;
+    // a transcoded string may be longer than its raw bytes but its output length is what the offsets say: write it
+    // straight to its place after the group's staged bytes are out (rare)
+    __syncwarp();
+    {
+      uint8_t* g = values + base;                                         // group's first output byte
+      const uint8_t* sb = s_stage[wid] + (uint32_t)(base & 3);
+      // head bytes up to 4-byte alignment, aligned words, tail bytes
+      const uint32_t headb = min(grp_bytes, (uint32_t)((4 - (base & 3)) & 3));
+      if (lane < headb) g[lane] = sb[lane];
+      const uint32_t nw = (grp_bytes - headb) >> 2;
+      const uint32_t* sw = reinterpret_cast<const uint32_t*>(sb + headb);  // 4-byte aligned: (base & 3) + headb = 0 mod 4
+      uint32_t* gw = reinterpret_cast<uint32_t*>(g + headb);
+      for (uint32_t i = lane; i < nw; i += 32) gw[i] = sw[i];
+      const uint32_t tailb = grp_bytes - headb - 4 * nw;
+      if (lane < tailb) g[headb + 4 * nw + lane] = sb[headb + 4 * nw + lane];
+    }
+    __syncwarp();
+    if (redo) transcode_cell(p, cnt0, values + (size_t)(uint32_t)off0 * w);
+    __syncwarp();
   }
 }
 
