@@ -337,6 +337,7 @@ struct tfr_decoder {
   bool fast_ok = false;
   size_t tile_smem_set = 0;
   int spec_state = 0;                   // 0 learning, 1 speculating on uniform shapes, -1 disabled
+  double mean_rec_bytes = 0.0;          // framed bytes per record of the previous batch (frame index chunk size)
   std::vector<int32_t> spec_len;
   DevBuf uniform_dev;
   int32_t* h_uniform = nullptr;         // pinned
@@ -479,13 +480,21 @@ static int32_t frame_stop_to_error(uint32_t stop, bool is_final) {
   }
 }
 
-static uint32_t pick_chunk_bytes(size_t nbytes, int sm_count) {
+static uint32_t pick_chunk_bytes(size_t nbytes, int sm_count, double mean_rec_bytes = 0.0) {
   // enough chunks to give every resident warp work, large enough to amortise the candidate search
   // the frame index costs one candidate search per chunk (the dominant part) plus one dependent DRAM hop per
   // record: aim for about one chunk per resident warp
   size_t want = (size_t)sm_count * 64;
   size_t c = 4096;
   while (c < 262144 && nbytes / c > want) c <<= 1;
+  // the chain walk costs one dependent DRAM hop per record, the candidate search about one record length per chunk: with
+  // the record size of the previous batch known, keep the chains at about 48 records (small records -> more, smaller chunks)
+  if (mean_rec_bytes > 0) {
+    size_t by_rec = 4096;
+    while (by_rec < 262144 && (double)by_rec < 48.0 * mean_rec_bytes) by_rec <<= 1;
+    while (by_rec < 262144 && nbytes / by_rec > 32768) by_rec <<= 1;
+    c = std::min(c, by_rec);
+  }
   return (uint32_t)c;
 }
 
@@ -737,7 +746,7 @@ static int32_t decode_impl(tfr_decoder* d, const void* data, size_t nbytes, int3
   fr.stop = FS_EOF;
   bool k1_verified = true;
   auto run_k1 = [&](bool verify_headers) -> int32_t {
-    C.chunk_bytes = pick_chunk_bytes(nbytes, d->ctx->sm_count);
+    C.chunk_bytes = pick_chunk_bytes(nbytes, d->ctx->sm_count, d->mean_rec_bytes);
     C.n_chunks = (uint32_t)((nbytes + C.chunk_bytes - 1) / C.chunk_bytes);
     TRY(d->chunks.ensure((size_t)C.n_chunks * sizeof(ChunkInfo)));
     TRY(d->chunk_base.ensure(((size_t)C.n_chunks + 1) * sizeof(uint32_t)));
@@ -776,6 +785,7 @@ static int32_t decode_impl(tfr_decoder* d, const void* data, size_t nbytes, int3
     CUDA_TRY(cudaGetLastError());
     fr = d->h_stats->frame;
     C.n = fr.n_records;
+    if (fr.n_records > 64) d->mean_rec_bytes = (double)nbytes / fr.n_records;     // next batch's chunk size
     C.rec_off_ready = false;
     k1_verified = verify_headers || !C.verify;
     return TFR_OK;
