@@ -167,3 +167,25 @@ def test_codec_names_and_extensions():
         with io._open_read(p) as f:
             assert f.read(5) == b"abcab" and f.read() == (b"abc" * 70000 + b"tail")[5:]
     assert zlib.decompress(open(os.path.join(d, "f.tfrecord.deflate"), "rb").read()) == b"abc" * 70000 + b"tail"
+
+
+def test_bench_corpus_is_the_parity_tests_corpus(oracle):
+    """bench.py carries its own copy of the configs[1] generator (our arm must not execute oracle/): same columns, same
+    framed bytes as the corpus the parity tests use; and the host-memory rule picks one batch size for every N"""
+    import importlib.util
+    from oracle.corpus import cfg2_columns
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py"))
+    b = importlib.util.module_from_spec(spec)
+    argv, sys.argv = sys.argv, ["bench.py"]
+    try:
+        spec.loader.exec_module(b)
+    finally:
+        sys.argv = argv
+    s1, c1 = b.cfg2_schema_and_columns(777, 99)
+    s2, c2 = cfg2_columns(777, seed=99)
+    assert s1.names == s2.names
+    d1, rc1, _ = oracle.encode(c1, s1)
+    d2, rc2, _ = oracle.encode(c2, s2)
+    assert rc1 == 0 and rc2 == 0 and d1 == d2
+    assert b.host_mem_available() is None or b.host_mem_available() > 0
+    assert b.host_cores() >= 1
