@@ -189,3 +189,11 @@ def test_bench_corpus_is_the_parity_tests_corpus(oracle):
     assert rc1 == 0 and rc2 == 0 and d1 == d2
     assert b.host_mem_available() is None or b.host_mem_available() > 0
     assert b.host_cores() >= 1
+
+
+def test_jni_shim_compiles_against_the_header():
+    """INTEGRATION.md's JNI shim cannot be built here (no JDK), but it must stay in step with include/tfrgpu.h: syntax- and
+    type-check it against a minimal stand-in for <jni.h>"""
+    p = subprocess.run(["g++", "-std=c++17", "-fsyntax-only", "-DTFR_BUILD_JNI", "-I", os.path.join(ROOT, "tests", "jni_stub"),
+                        os.path.join(ROOT, "spark-tfrecord_b200", "jni", "tfrgpu_jni.cpp")], capture_output=True, text=True, timeout=120)
+    assert p.returncode == 0, p.stderr[-3000:]
