@@ -24,7 +24,7 @@ struct CrcTables {
   uint32_t t0[256];
   uint32_t k128[4][256];
   uint32_t xw[40];
-  uint32_t s8[8][256];   // slicing-by-8 tables (tile.cuh: one record per thread, serial CRC from shared memory)
+  uint32_t s8[8][256];   // slicing-by-8 tables (source of the 5-bit tables below; the tile kernels use g5)
   // tile.cuh: the 8-byte fold through 5-BIT tables.  A 32-entry table is one word per shared-memory bank, so a lookup
   // is conflict-free whatever the 32 lanes index (a 256-entry table costs ~3 wavefronts per lookup with random bytes).
   //   g5[k*32 + v], k = 0..12: contribution of bits 5k..5k+4 (= v) of the 64-bit block to the state 8 bytes later

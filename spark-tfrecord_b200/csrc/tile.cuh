@@ -212,7 +212,7 @@ template <bool SEQ>
 __global__ void __launch_bounds__(TILE_THREADS, TILE_MIN_CTAS) decode_tile_kernel(TileArgs A) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
-  uint32_t* s8 = reinterpret_cast<uint32_t*>(smem_raw + 16);                               // g5 tables, then xp512
+  uint32_t* s8 = reinterpret_cast<uint32_t*>(smem_raw + 16);                               // g5 tables, then xp16
   uint32_t* sseen = reinterpret_cast<uint32_t*>(smem_raw + 16 + TILE_CRC_BYTES);                 // [32 rows][4 words], zero in the consts blob
   const uint32_t nf = (uint32_t)A.sch.n_fields;
   uint8_t* sbase = smem_raw + 16 + TILE_CRC_BYTES + TILE_SEEN_BYTES;
