@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define TFR_ABI_VERSION 1
+#define TFR_ABI_VERSION 2
 
 /* ---- status codes (SURVEY.md section 8b "error conventions") ------------------------- */
 enum {
@@ -110,24 +110,42 @@ void    tfr_decoder_destroy(tfr_decoder*);
 
 /* Pinned host staging the caller fills with framed file bytes (the JVM sees it as a direct
  * ByteBuffer).  Grows on demand; the pointer stays valid until the next call that needs
- * more capacity or destroy.                                                                */
+ * more capacity or destroy.  A decoder has tfr_decoder_num_staging_slots() such buffers so
+ * that block t+1 can be read from the file while block t is in flight (tfr_decode_submit);
+ * a slot may be refilled once the batch decoded from it has been waited on.
+ * tfr_decoder_staging is slot 0.                                                           */
 int32_t tfr_decoder_staging(tfr_decoder*, size_t min_bytes, void** host_ptr, size_t* capacity);
+int32_t tfr_decoder_staging_slot(tfr_decoder*, int32_t slot, size_t min_bytes, void** host_ptr, size_t* capacity);
+int32_t tfr_decoder_num_staging_slots(void);
 
 /* The hot path.  Replaces the per-record loop recordReader.nextKeyValue -> parseFrom ->
  * deserializeExample (M/TFRecordFileReader.scala:49-81, M/TFRecordDeserializer.scala:21-61).
  *   data/nbytes : framed TFRecord bytes (u64 len | u32 maskedcrc(len) | payload | u32 maskedcrc)
  *                 starting at a record boundary; in host memory (pageable or the pinned
- *                 staging above) or in device memory (data_on_device != 0; any alignment is
- *                 accepted, a 16-byte aligned pointer gets the single-pass tile kernels).
+ *                 staging above) or in device memory (data_on_device != 0).  Device input: any
+ *                 alignment is accepted (a 16-byte aligned pointer gets the single-pass tile
+ *                 kernels) and NO padding behind data + nbytes is required: the kernels never
+ *                 touch a 4-byte aligned word that holds no byte of the buffer.  The buffer must
+ *                 stay valid and unchanged until the batch has been waited on.
  *   is_final    : nonzero -> a trailing partial record is TFR_E_TRUNCATED (EOF inside a
  *                 record); zero -> it is left unconsumed (see *consumed).
- * Work is enqueued on the decoder's stream; the call returns after the stage that needs
- * host-visible sizes (one small D2H) and the batch is complete when tfr_batch_wait returns.
+ * tfr_decode returns when the batch is complete and verified (*consumed is final).
  * A data error does not fail the call: rows before the first bad record are delivered and
  * the error is reported by tfr_batch_status, like the reference's iterator which yields
- * rows until the throwing record.                                                          */
+ * rows until the throwing record.
+ *
+ * tfr_decode_submit is the pipelined form: it enqueues the copy, the frame index and the decode
+ * and returns without waiting.  Once a decoder has seen its first batches (record size and
+ * column shapes learned) this involves no host/device synchronisation at all; the batch's
+ * result, including consumed_bytes, is available after tfr_batch_wait / tfr_batch_status /
+ * tfr_batch_columns / tfr_batch_to_host, which also redo -- transparently, with identical
+ * results -- any batch the single-pass kernels could not vouch for.  At most
+ * tfr_decoder_num_staging_slots() submitted batches are in flight per decoder; a further
+ * submit first waits for the oldest one.                                                   */
 int32_t tfr_decode(tfr_decoder*, const void* data, size_t nbytes, int32_t data_on_device,
                    int32_t is_final, tfr_batch** out, size_t* consumed);
+int32_t tfr_decode_submit(tfr_decoder*, const void* data, size_t nbytes, int32_t data_on_device,
+                          int32_t is_final, tfr_batch** out);
 
 int32_t tfr_decoder_stream(tfr_decoder*, void** cuda_stream /* cudaStream_t */);
 
@@ -142,6 +160,10 @@ int32_t tfr_decoder_stream(tfr_decoder*, void** cuda_stream /* cudaStream_t */);
 int32_t tfr_decoder_set_profiling(tfr_decoder*, int32_t enable);
 int32_t tfr_decoder_get_profile(tfr_decoder*, double* ms /* [TFR_PROFILE_STAGES] */, int64_t* kernel_launches,
                                 int64_t* pass1_launches);
+/* counters since creation: [0] batches decoded, [1] submitted speculatively (no host sync), [2] of those redone after
+ * the device raised a flag, [3] batches through count mode (ragged / learning), [4] through the general kernels,
+ * [5] column shapes (re)learned                                                                                   */
+int32_t tfr_decoder_get_stats(tfr_decoder*, int64_t* out, int32_t n /* <= 8 */);
 
 int32_t tfr_batch_wait(tfr_batch*);
 typedef struct tfr_batch_info {
@@ -177,8 +199,11 @@ typedef struct tfr_column {
 int32_t tfr_batch_num_columns(tfr_batch*);
 /* device-resident view (zero copy; valid until tfr_batch_release) */
 int32_t tfr_batch_columns(tfr_batch*, tfr_column* out, int32_t n);
-/* copies every buffer to pinned host memory owned by the batch (D2H on the decoder
- * stream, synchronised) -- the path a row-based InternalRow consumer uses                  */
+/* copies every buffer to pinned host memory owned by the batch (D2H on the decoder's
+ * copy-out stream) -- the path a row-based InternalRow consumer uses.  tfr_batch_to_host_async
+ * only enqueues the copy behind the batch's kernels (so that it overlaps the next batch's
+ * H2D and decode); tfr_batch_to_host waits for it and returns the host view.               */
+int32_t tfr_batch_to_host_async(tfr_batch*);
 int32_t tfr_batch_to_host(tfr_batch*, tfr_column* out, int32_t n);
 /* Arrow C Data Interface export of one column from the host copy (struct ArrowArray /
  * struct ArrowSchema from arrow/c/abi.h, passed as void* to keep this header standalone);
@@ -213,8 +238,12 @@ enum { TFR_INF_NULL = 0, TFR_INF_LONG = 1, TFR_INF_FLOAT = 2, TFR_INF_STRING = 3
        TFR_INF_ARR2_NULL = 10 /* ArrayType(ArrayType(null)): a FeatureList whose steps are all empty (:102-107) */ };
 typedef struct tfr_infer tfr_infer;
 int32_t tfr_infer_create(int32_t record_type, int32_t device, tfr_infer** out);
-/* accumulate one block of framed bytes (seqOp of rdd.aggregate, :40,43) */
+/* accumulate one block of framed bytes (seqOp of rdd.aggregate, :40,43).  tfr_infer_update takes a whole
+ * file (a trailing partial record is TFR_E_TRUNCATED); tfr_infer_update_block streams a file of any size in
+ * blocks below 2 GiB with the tfr_decode contract (is_final / *consumed).                                  */
 int32_t tfr_infer_update(tfr_infer*, const void* data, size_t nbytes, int32_t data_on_device);
+int32_t tfr_infer_update_block(tfr_infer*, const void* data, size_t nbytes, int32_t data_on_device,
+                               int32_t is_final, size_t* consumed);
 /* number of distinct feature names seen so far, then the (name, code) pairs; names are
  * returned sorted bytewise so that ranks can merge them deterministically               */
 int32_t tfr_infer_result(tfr_infer*, int32_t* n_names);

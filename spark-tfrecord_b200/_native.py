@@ -21,11 +21,12 @@ _LIB = None
 # every symbol include/tfrgpu.h declares
 EXPORTS = [
     "tfr_abi_version", "tfr_status_string", "tfr_last_error", "tfr_schema_create", "tfr_schema_destroy",
-    "tfr_schema_num_fields", "tfr_decoder_create", "tfr_decoder_destroy", "tfr_decoder_staging", "tfr_decode",
-    "tfr_decoder_stream", "tfr_decoder_set_profiling", "tfr_decoder_get_profile", "tfr_batch_wait", "tfr_batch_status", "tfr_batch_num_columns", "tfr_batch_columns",
-    "tfr_batch_to_host", "tfr_batch_export_arrow_host", "tfr_batch_export_arrow_device", "tfr_batch_release",
+    "tfr_schema_num_fields", "tfr_decoder_create", "tfr_decoder_destroy", "tfr_decoder_staging", "tfr_decoder_staging_slot",
+    "tfr_decoder_num_staging_slots", "tfr_decode", "tfr_decode_submit",
+    "tfr_decoder_stream", "tfr_decoder_set_profiling", "tfr_decoder_get_profile", "tfr_decoder_get_stats", "tfr_batch_wait", "tfr_batch_status", "tfr_batch_num_columns", "tfr_batch_columns",
+    "tfr_batch_to_host_async", "tfr_batch_to_host", "tfr_batch_export_arrow_host", "tfr_batch_export_arrow_device", "tfr_batch_release",
     "tfr_encoder_create", "tfr_encoder_destroy", "tfr_encode", "tfr_encoder_result_host", "tfr_encoder_stream",
-    "tfr_infer_create", "tfr_infer_update", "tfr_infer_result", "tfr_infer_name", "tfr_infer_destroy",
+    "tfr_infer_create", "tfr_infer_update", "tfr_infer_update_block", "tfr_infer_result", "tfr_infer_name", "tfr_infer_destroy",
 ]
 
 
@@ -103,7 +104,13 @@ def lib():
         "tfr_decoder_create": (i32, [vp, i32, u32, P(vp)]),
         "tfr_decoder_destroy": (None, [vp]),
         "tfr_decoder_staging": (i32, [vp, sz, P(vp), P(sz)]),
+        "tfr_decoder_staging_slot": (i32, [vp, i32, sz, P(vp), P(sz)]),
+        "tfr_decoder_num_staging_slots": (i32, []),
         "tfr_decode": (i32, [vp, vp, sz, i32, i32, P(vp), P(sz)]),
+        "tfr_decode_submit": (i32, [vp, vp, sz, i32, i32, P(vp)]),
+        "tfr_decoder_get_stats": (i32, [vp, P(i64), i32]),
+        "tfr_batch_to_host_async": (i32, [vp]),
+        "tfr_infer_update_block": (i32, [vp, vp, sz, i32, i32, P(sz)]),
         "tfr_decoder_stream": (i32, [vp, P(vp)]),
         "tfr_decoder_set_profiling": (i32, [vp, i32]),
         "tfr_decoder_get_profile": (i32, [vp, P(C.c_double), P(i64), P(i64)]),
@@ -182,16 +189,33 @@ def _device_ptr(obj):
 
 
 class Batch:
-    def __init__(self, h, ncols):
+    """A decoded batch.  After Decoder.submit() the result is not known yet: `info` / `n_rows` (and every accessor
+    below) wait for it on first use (tfr_batch_status resolves a pipelined batch)."""
+
+    def __init__(self, h, ncols, keep=None):
         self.h = h
         self.ncols = ncols
-        info = tfr_batch_info()
-        _check(lib().tfr_batch_status(h, C.byref(info)))
-        self.info = {k: getattr(info, k) for k, _ in tfr_batch_info._fields_}
-        self.n_rows = self.info["n_rows"]
+        self._info = None
+        self._keep = keep          # the input buffer of a pipelined batch must outlive it
+
+    @property
+    def info(self) -> dict:
+        if self._info is None:
+            info = tfr_batch_info()
+            _check(lib().tfr_batch_status(self.h, C.byref(info)))
+            self._info = {k: getattr(info, k) for k, _ in tfr_batch_info._fields_}
+        return self._info
+
+    @property
+    def n_rows(self) -> int:
+        return self.info["n_rows"]
 
     def wait(self):
         _check(lib().tfr_batch_wait(self.h))
+
+    def to_host_async(self):
+        """enqueue the D2H of every Arrow buffer behind the batch's kernels (overlaps the next batch)"""
+        _check(lib().tfr_batch_to_host_async(self.h))
 
     def device_columns(self) -> List[tfr_column]:
         cols = (tfr_column * max(self.ncols, 1))()
@@ -249,6 +273,22 @@ class Decoder:
         _check(lib().tfr_decoder_staging(self.h, nbytes, C.byref(p), C.byref(cap)))
         return np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_uint8)), shape=(cap.value,))
 
+    def staging_slot(self, slot: int, nbytes: int) -> np.ndarray:
+        p = C.c_void_p()
+        cap = C.c_size_t()
+        _check(lib().tfr_decoder_staging_slot(self.h, slot, nbytes, C.byref(p), C.byref(cap)))
+        return np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_uint8)), shape=(cap.value,))
+
+    @staticmethod
+    def num_staging_slots() -> int:
+        return lib().tfr_decoder_num_staging_slots()
+
+    def stats(self) -> dict:
+        v = (C.c_int64 * 8)()
+        _check(lib().tfr_decoder_get_stats(self.h, v, 8))
+        names = ["batches", "speculative_submits", "speculative_redone", "count_mode_batches", "general_path_batches", "shapes_learned"]
+        return {k: v[i] for i, k in enumerate(names)}
+
     def stream(self) -> int:
         p = C.c_void_p()
         _check(lib().tfr_decoder_stream(self.h, C.byref(p)))
@@ -274,6 +314,15 @@ class Decoder:
         used = C.c_size_t()
         _check(lib().tfr_decode(self.h, ptr, n, on_dev, 1 if is_final else 0, C.byref(b), C.byref(used)))
         return Batch(b, self.ncols), used.value
+
+    def submit(self, data, is_final: bool = True, nbytes: Optional[int] = None) -> "Batch":
+        """pipelined decode (tfr_decode_submit): returns at once; Batch.info["consumed_bytes"] has the consumed count"""
+        ptr, n, on_dev, keep = _device_ptr(data)
+        if nbytes is not None:
+            n = nbytes
+        b = C.c_void_p()
+        _check(lib().tfr_decode_submit(self.h, ptr, n, on_dev, 1 if is_final else 0, C.byref(b)))
+        return Batch(b, self.ncols, keep)
 
     def close(self):
         if self.h:
@@ -349,6 +398,15 @@ class Infer:
     def update(self, data):
         ptr, n, on_dev, keep = _device_ptr(data)
         _check(lib().tfr_infer_update(self.h, ptr, n, on_dev))
+
+    def update_block(self, data, is_final: bool, nbytes: Optional[int] = None) -> int:
+        """one block of a streamed file (tfr_infer_update_block) -> consumed bytes"""
+        ptr, n, on_dev, keep = _device_ptr(data)
+        if nbytes is not None:
+            n = nbytes
+        used = C.c_size_t()
+        _check(lib().tfr_infer_update_block(self.h, ptr, n, on_dev, 1 if is_final else 0, C.byref(used)))
+        return used.value
 
     def result(self) -> dict:
         n = C.c_int32()

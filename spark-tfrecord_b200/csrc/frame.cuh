@@ -14,6 +14,8 @@
 //                     themselves contain TFRecord streams, corruption): one warp re-chains the
 //                     affected chunks sequentially from the true position -- always exact.
 //   4. chunk counts are prefix-summed and frame_emit re-walks each chunk writing rec_off[].
+// Four launches per batch: frame_search (candidates, also resets the result block), frame_scan (chains),
+// frame_link (one block: link check + repair + stop + count prefix + result; steps 2-4 above) and frame_emit.
 // The result is identical to the sequential scan for every input, including the error cases
 // (bad length CRC, truncated tail, oversize length) which are reported at the first bad record.
 #pragma once
@@ -91,9 +93,13 @@ __device__ __forceinline__ uint32_t frame_chain(const uint32_t* t0, const uint8_
 // __ballot_sync picks the first hit.  The first 2 KiB of the chunk are prefetched by 16 lanes up front so the
 // steps hit L1 instead of paying one dependent DRAM miss per 128-byte line.
 __global__ void __launch_bounds__(256) frame_search_kernel(const uint8_t* __restrict__ data, uint32_t nbytes, uint32_t chunk_bytes,
-                                                           uint32_t n_chunks, const CrcTables* __restrict__ tabs, uint32_t* __restrict__ first_out) {
+                                                           uint32_t n_chunks, const CrcTables* __restrict__ tabs, uint32_t* __restrict__ first_out,
+                                                           uint32_t* __restrict__ reset_words, uint32_t n_reset) {
   __shared__ uint32_t t0[256];
   for (int i = threadIdx.x; i < 256; i += blockDim.x) t0[i] = tabs->t0[i];
+  // block 0 also resets the per-batch result block (FrameResult, tile flags, null counters ...) that the later kernels of
+  // this batch accumulate into: one launch less than a memset, and stream order puts it in front of all of them
+  if (blockIdx.x == 0) for (uint32_t i = threadIdx.x; i < n_reset; i += blockDim.x) reset_words[i] = 0u;
   __syncthreads();
   const uint32_t lane = threadIdx.x & 31;
   const uint32_t warps_per_block = blockDim.x >> 5;
@@ -128,7 +134,7 @@ __global__ void __launch_bounds__(256) frame_search_kernel(const uint8_t* __rest
 __global__ void __launch_bounds__(128) frame_scan_kernel(const uint8_t* __restrict__ data, uint32_t nbytes, uint32_t chunk_bytes,
                                                          uint32_t n_chunks, uint32_t verify, const CrcTables* __restrict__ tabs,
                                                          const uint32_t* __restrict__ first_in, ChunkInfo* __restrict__ chunks,
-                                                         uint32_t* __restrict__ chunk_cnt, uint32_t* __restrict__ stage, FrameResult* __restrict__ res) {
+                                                         uint32_t* __restrict__ stage, FrameResult* __restrict__ res) {
   __shared__ uint32_t t0[256];
   for (int i = threadIdx.x; i < 256; i += blockDim.x) t0[i] = tabs->t0[i];
   __syncthreads();
@@ -146,30 +152,23 @@ __global__ void __launch_bounds__(128) frame_scan_kernel(const uint8_t* __restri
     if (mx) atomicMax(&res->max_len, mx);                                  // a false candidate can only enlarge the bound
   }
   chunks[k] = ci;
-  chunk_cnt[k] = ci.count;
 }
 
-// link check: chunk k (k >= 1) is consistent iff the previous chunk's chain left exactly onto its guess
-__global__ void frame_check_kernel(const ChunkInfo* __restrict__ chunks, uint32_t n_chunks, FrameResult* __restrict__ res) {
-  uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
-  if (k == 0 || k >= n_chunks) return;
-  ChunkInfo prev = chunks[k - 1], cur = chunks[k];
-  bool ok = prev.stop == FS_LEFT && cur.first != 0xffffffffu && prev.end == cur.first;
-  // a previous chunk that already stopped the stream makes every later chunk irrelevant; that is
-  // resolved in frame_finish, but it still has to go through the sequential path
-  if (!ok) atomicMin(&res->first_bad, k);
-}
-
-// sequential, exact: single warp (lane 0 does the work; the warp form keeps the launch shape simple).
-// Starts at the first broken link and re-chains until the speculation re-synchronises.
-__global__ void frame_repair_kernel(const uint8_t* __restrict__ data, uint32_t nbytes, uint32_t chunk_bytes, uint32_t n_chunks,
-                                    uint32_t verify, const CrcTables* __restrict__ tabs, ChunkInfo* __restrict__ chunks,
-                                    uint32_t* __restrict__ chunk_cnt, uint32_t* __restrict__ stage, FrameResult* __restrict__ res) {
-  __shared__ uint32_t t0[256];
-  for (int i = threadIdx.x; i < 256; i += blockDim.x) t0[i] = tabs->t0[i];
-  __syncthreads();
-  if (res->first_bad == 0xffffffffu || threadIdx.x != 0) return;
-  uint32_t k = res->first_bad;          // >= 1
+// K1c -- link check + repair + stop + count prefix + result, ONE block (the chunk table is a few hundred KB at most).
+//   link check : chunk k (k >= 1) is consistent iff the previous chunk's chain left exactly onto its guess; a previous
+//                chunk that already stopped the stream makes every later chunk irrelevant (they are cleared by the repair)
+//   repair     : sequential, exact (thread 0): starts at the first broken link and re-chains until the speculation
+//                re-synchronises
+//   stop       : the first (and, after the repair, only) chunk whose chain did not leave the chunk
+//   prefix     : chunk_base[k] = records that start before chunk k (n_chunks + 1 entries)
+//   result     : FrameResult.  With `verify_stop` (the chains ran without header verification because the tile kernel
+//                checks every length CRC of the records it is given) the header the stream stopped on is checked here: a
+//                corrupt length must be a length-CRC error (the reference checks the CRC first), never a "partial tail"
+//                or an oversize length.
+__device__ __forceinline__ void frame_repair(const uint32_t* t0, const uint8_t* __restrict__ data, uint32_t nbytes, uint32_t chunk_bytes, uint32_t n_chunks,
+                                             bool verify, ChunkInfo* __restrict__ chunks, uint32_t* __restrict__ stage, uint32_t first_bad,
+                                             FrameResult* __restrict__ res) {
+  uint32_t k = first_bad;               // >= 1
   uint32_t repairs = 0;
   ChunkInfo prev = chunks[k - 1];
   uint32_t F = prev.end;                // true position where the stream continues
@@ -179,46 +178,95 @@ __global__ void frame_repair_kernel(const uint8_t* __restrict__ data, uint32_t n
     const uint32_t ce = (nbytes - cs > chunk_bytes) ? cs + chunk_bytes : nbytes;
     ChunkInfo ci = chunks[k];
     if (stopped || F >= ce) {           // no record starts in this chunk
-      if (ci.first != 0xffffffffu || ci.count) { ci.first = 0xffffffffu; ci.count = 0; ci.stop = FS_NONE; ci.end = F; chunks[k] = ci; chunk_cnt[k] = 0; ++repairs; }
+      if (ci.first != 0xffffffffu || ci.count) { ci.first = 0xffffffffu; ci.count = 0; ci.stop = FS_NONE; ci.end = F; chunks[k] = ci; ++repairs; }
       continue;
     }
     if (ci.first == F) {                // speculation is right from here on: re-synchronised
       if (ci.stop != FS_LEFT) { stopped = true; continue; }
-      // the following chunks were checked against this chunk's end by frame_check; if one of them is
-      // broken again the loop keeps going, otherwise everything behind is already consistent.
-      F = ci.end;
-      // fast-forward over consistent chunks
+      F = ci.end;                       // a later broken link keeps the loop going; consistent chunks are fast-forwarded
       continue;
     }
     uint32_t q = F, cnt = 0, mx = 0;
     ci.first = F;
-    ci.stop = frame_chain(t0, data, nbytes, ce, verify != 0, q, cnt, mx, stage + (size_t)k * FRAME_STAGE);
-    if (mx) atomicMax(&res->max_len, mx);
+    ci.stop = frame_chain(t0, data, nbytes, ce, verify, q, cnt, mx, stage + (size_t)k * FRAME_STAGE);
+    if (mx > res->max_len) res->max_len = mx;
     ci.end = q; ci.count = cnt;
-    chunks[k] = ci; chunk_cnt[k] = cnt; ++repairs;
+    chunks[k] = ci; ++repairs;
     if (ci.stop != FS_LEFT) stopped = true; else F = q;
   }
   res->repairs = repairs;
 }
 
-// stream stop reason + record count (the chunk counts are prefix-summed by scan.cuh's kernels into chunk_base)
-__global__ void frame_stop_kernel(const ChunkInfo* __restrict__ chunks, uint32_t n_chunks, uint32_t* __restrict__ stop_chunk) {
-  uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
-  if (k >= n_chunks) return;
-  ChunkInfo ci = chunks[k];
-  if (ci.first != 0xffffffffu && ci.stop != FS_LEFT) atomicMin(stop_chunk, k);
-}
-__global__ void frame_finish_kernel(const ChunkInfo* __restrict__ chunks, uint32_t n_chunks, uint32_t nbytes,
-                                    const uint32_t* __restrict__ chunk_base, const uint32_t* __restrict__ stop_chunk, FrameResult* __restrict__ res) {
-  if (threadIdx.x || blockIdx.x) return;
-  // records that start after the stop chunk do not exist (repair cleared them); the stop chunk is the first (and only)
+#define FRAME_LINK_THREADS 1024
+__global__ void __launch_bounds__(FRAME_LINK_THREADS) frame_link_kernel(const uint8_t* __restrict__ data, uint32_t nbytes, uint32_t chunk_bytes,
+                                                                        uint32_t n_chunks, uint32_t verify, uint32_t verify_stop,
+                                                                        const CrcTables* __restrict__ tabs, ChunkInfo* __restrict__ chunks,
+                                                                        uint32_t* __restrict__ stage, uint32_t* __restrict__ chunk_base,
+                                                                        FrameResult* __restrict__ res) {
+  __shared__ uint32_t t0[256];
+  __shared__ uint32_t s_first_bad, s_stop_chunk, s_carry;
+  __shared__ uint32_t wsum[FRAME_LINK_THREADS / 32];
+  const uint32_t tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  for (uint32_t i = tid; i < 256; i += blockDim.x) t0[i] = tabs->t0[i];
+  if (tid == 0) { s_first_bad = 0xffffffffu; s_stop_chunk = 0xffffffffu; s_carry = 0; }
+  __syncthreads();
+  if (n_chunks == 0) {
+    if (tid == 0) { res->n_records = 0; res->stop = FS_EOF; res->stop_pos = 0; res->first_bad = 0xffffffffu; chunk_base[0] = 0; }
+    return;
+  }
+  for (uint32_t k = tid + 1; k < n_chunks; k += blockDim.x) {
+    const ChunkInfo prev = chunks[k - 1], cur = chunks[k];
+    if (!(prev.stop == FS_LEFT && cur.first != 0xffffffffu && prev.end == cur.first)) atomicMin(&s_first_bad, k);
+  }
+  __syncthreads();
+  if (tid == 0) {
+    res->first_bad = s_first_bad;
+    if (s_first_bad != 0xffffffffu) frame_repair(t0, data, nbytes, chunk_bytes, n_chunks, verify != 0, chunks, stage, s_first_bad, res);
+    __threadfence_block();
+  }
+  __syncthreads();
+  // exclusive prefix of the chunk counts + the stop chunk
+  for (uint32_t base = 0; base < n_chunks; base += blockDim.x) {
+    const uint32_t k = base + tid;
+    uint32_t c = 0;
+    if (k < n_chunks) {
+      const ChunkInfo ci = chunks[k];
+      c = ci.count;
+      if (ci.first != 0xffffffffu && ci.stop != FS_LEFT) atomicMin(&s_stop_chunk, k);
+    }
+    uint32_t x = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(FULLMASK, x, o); if (lane >= (uint32_t)o) x += y; }
+    if (lane == 31) wsum[wid] = x;
+    __syncthreads();
+    if (wid == 0) {
+      uint32_t w = wsum[lane];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(FULLMASK, w, o); if (lane >= (uint32_t)o) w += y; }
+      wsum[lane] = w;
+    }
+    __syncthreads();
+    const uint32_t excl = x - c + (wid ? wsum[wid - 1] : 0u) + s_carry;
+    if (k < n_chunks) chunk_base[k] = excl;
+    __syncthreads();
+    if (tid == blockDim.x - 1) s_carry = excl + c;
+    __syncthreads();
+  }
+  if (tid != 0) return;
+  chunk_base[n_chunks] = s_carry;
+  // records that start after the stop chunk do not exist (the repair cleared them); the stop chunk is the first (and only)
   // chunk with a non-LEFT stop
-  uint32_t sc = *stop_chunk;
-  if (n_chunks == 0) { res->n_records = 0; res->stop = FS_EOF; res->stop_pos = 0; return; }
-  if (sc == 0xffffffffu) { res->n_records = chunk_base[n_chunks]; res->stop = FS_EOF; res->stop_pos = nbytes; return; }   // cannot happen for nbytes > 0
-  ChunkInfo ci = chunks[sc];
+  const uint32_t sc = s_stop_chunk;
+  if (sc == 0xffffffffu) { res->n_records = s_carry; res->stop = FS_EOF; res->stop_pos = nbytes; return; }   // cannot happen for nbytes > 0
+  const ChunkInfo ci = chunks[sc];
+  uint32_t stop = ci.stop;
+  if (verify_stop && (stop == FS_PART_REC || stop == FS_TOO_LARGE)) {
+    const uint32_t q = ci.end;                      // >= 12 bytes are left at q for both stops
+    const uint32_t lo = load_u32_unaligned(data + q), hi = load_u32_unaligned(data + q + 4);
+    if (crc_mask(crc_u64(t0, lo, hi)) != load_u32_unaligned(data + q + 8)) stop = FS_BAD_CRC;
+  }
   res->n_records = chunk_base[sc] + ci.count;
-  res->stop = ci.stop; res->stop_pos = ci.end;
+  res->stop = stop; res->stop_pos = ci.end;
 }
 
 // rec_off[] from the staged offsets: FRAME_EMIT_LANES threads per chunk copy (coalesced), chains longer than the
@@ -226,8 +274,9 @@ __global__ void frame_finish_kernel(const ChunkInfo* __restrict__ chunks, uint32
 #define FRAME_EMIT_LANES 8u
 __global__ void __launch_bounds__(256) frame_emit_kernel(const uint8_t* __restrict__ data, const ChunkInfo* __restrict__ chunks,
                                                          const uint32_t* __restrict__ chunk_base, uint32_t n_chunks, const uint32_t* __restrict__ stage,
-                                                         const FrameResult* __restrict__ res, uint32_t* __restrict__ rec_off) {
+                                                         const FrameResult* __restrict__ res, uint32_t* __restrict__ rec_off, uint32_t cap) {
   const uint32_t n = res->n_records;
+  if (n > cap) return;                       // more records than rec_off was sized for (speculative submit): the host redoes the batch
   const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t == 0) rec_off[n] = res->stop_pos;
   const uint32_t k = t / FRAME_EMIT_LANES, sub = t % FRAME_EMIT_LANES;

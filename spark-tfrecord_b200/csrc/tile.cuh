@@ -31,6 +31,8 @@
 //      finish them), or -- once the decoder has learned that every such column has a uniform shape
 //      (FloatList[8], 16-byte BytesList ...) -- write the values at row * L in the same pass and only
 //      verify the shape ("uniform-shape speculation": input read once, output written once).
+//   5. the row count can be read from the device (TileArgs::n_dev = the frame index's result): the host enqueues the
+//      kernel without knowing it, with a grid sized from a capacity; surplus CTAs exit at once.
 #pragma once
 #include "common.cuh"
 #include "decode.cuh"
@@ -61,7 +63,10 @@ struct TileArgs {
   const uint8_t* data;
   uint32_t nbytes;
   const uint32_t* rec_off;      // [n+1]
-  uint32_t n;                   // rows in the batch (stride of the scratch arrays)
+  uint32_t n;                   // rows in the batch = stride of the scratch arrays; with n_dev: the CAPACITY the host sized everything for
+  const uint32_t* n_dev;        // non-null: the number of rows is read here (FrameResult::n_records of this batch, still on the device when the
+                                // kernel is enqueued); more rows than `n` raise TF_OVERFLOW and nothing is decoded
+  int32_t* const* offs0;        // [n_var * 3] Arrow offsets arrays; uniform columns get offs[i] = i * L from this kernel
   uint32_t tile_cap;            // bytes of shared memory reserved for the record bytes of one tile (TILE_ROWS slots)
   uint32_t slot;                // bytes per record slot: an ODD multiple of 16 (bank-group spread, see crc_chunks)
   uint32_t verify;
@@ -81,7 +86,7 @@ struct TileArgs {
   uint32_t* flags;              // [0] bit0: fall back to the general path, bit1: a uniform-shape speculation failed
 };
 
-enum { TF_FALLBACK = 1u, TF_SHAPE = 2u };
+enum { TF_FALLBACK = 1u, TF_SHAPE = 2u, TF_OVERFLOW = 4u };
 
 // ---- mbarrier + bulk async copy (PTX; sm_90+) ---------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -225,13 +230,26 @@ __global__ void __launch_bounds__(TILE_THREADS, TILE_MIN_CTAS) decode_tile_kerne
   // Record r of the tile is copied into its own slot: bytes [off_r & ~15, off_r + framed length) -> tile + r * slot.
   // (cp.async.bulk wants 16-byte aligned source, destination and size; the record starts (off_r & 15) bytes into its slot.)
   const uint32_t row0 = blockIdx.x * TILE_ROWS;
-  const uint32_t rows = min((uint32_t)TILE_ROWS, A.n - row0);
+  uint32_t n_rows = A.n;
+  if (A.n_dev) {
+    n_rows = *A.n_dev;
+    if (n_rows > A.n) {                                                    // more records than the host provisioned for: the host redoes the batch
+      if (blockIdx.x == 0 && threadIdx.x == 0) atomicOr(A.flags, TF_OVERFLOW | TF_FALLBACK);
+      return;
+    }
+    if (row0 >= n_rows) return;                                            // the grid was sized from the capacity
+  }
+  const uint32_t rows = min((uint32_t)TILE_ROWS, n_rows - row0);
   const bool active = lane < rows;
   const uint32_t row = row0 + lane;
   uint32_t off = 0, flen = 16;
   if (active) { off = A.rec_off[row]; flen = A.rec_off[row + 1] - off; }
   const uint32_t head = off & 15u;
-  const uint32_t cbytes = active ? (head + flen + 15u) & ~15u : 0u;       // may read < 16 bytes past the end (input buffers are padded)
+  const uint32_t cbytes = active ? (head + flen + 15u) & ~15u : 0u;
+  // the last 16-byte group of the batch's last record may cross data + nbytes: a caller's device buffer need not be padded,
+  // so that group is clipped from the bulk copy and its bytes inside the buffer are moved with ordinary loads
+  const bool clip = active && (off - head) + cbytes > A.nbytes;
+  const uint32_t bulk_bytes = clip ? (A.nbytes - (off - head)) & ~15u : cbytes;
   if (__any_sync(FULLMASK, cbytes + 32u > A.slot)) {                       // a record too large for its slot: general path
     if (threadIdx.x == 0) atomicOr(A.flags, TF_FALLBACK);
     return;
@@ -241,13 +259,14 @@ __global__ void __launch_bounds__(TILE_THREADS, TILE_MIN_CTAS) decode_tile_kerne
       mbar_init(bar, 1);
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    const uint32_t total = __reduce_add_sync(FULLMASK, cbytes);
+    const uint32_t total = __reduce_add_sync(FULLMASK, bulk_bytes);
     if (lane == 0) {
       mbar_expect_tx(bar, total + A.const_bytes);
       bulk_g2s(smem_raw + 16, A.consts, A.const_bytes, bar);      // CRC tables, zeroed seen words, schema, templates, names
     }
     __syncwarp();
-    if (cbytes) bulk_g2s(tile_b + lane * A.slot, A.data + (off - head), cbytes, bar);
+    if (bulk_bytes) bulk_g2s(tile_b + lane * A.slot, A.data + (off - head), bulk_bytes, bar);
+    if (clip) for (uint32_t i = (off - head) + bulk_bytes; i < A.nbytes; ++i) tile_b[lane * A.slot + (i - (off - head))] = A.data[i];
   }
   __syncthreads();                                                // the barrier is initialised before anyone waits on it
   mbar_wait(bar, 0);
@@ -696,6 +715,15 @@ __global__ void __launch_bounds__(TILE_THREADS, TILE_MIN_CTAS) decode_tile_kerne
       const uint32_t wsel = f < 32 ? all[0] : f < 64 ? all[1] : f < 96 ? all[2] : all[3];
       const bool present = (wsel >> (f & 31)) & 1;
       const uint32_t m = __ballot_sync(FULLMASK, present && active);
+      if (A.offs0 && active && sfields[f].var_slot >= 0) {
+        // Arrow offsets of a uniform column are row * L: written here (coalesced, 32 rows per store), not by a separate launch
+        const int32_t vs = sfields[f].var_slot, ul = A.uniform_len[vs];
+        if (ul >= 0) {
+          int32_t* o = A.offs0[vs * 3];
+          o[row] = (int32_t)(row * (uint32_t)ul);
+          if (row + 1 == n_rows) o[n_rows] = (int32_t)(n_rows * (uint32_t)ul);
+        }
+      }
       if (active && !present && sfields[f].elem_type != TFR_T_NULL) {
         const DevField& fd = sfields[f];
         if (!fd.nullable) bad = true;                                         // NullPointerException: error path

@@ -1,0 +1,347 @@
+"""Parity at BENCH scale and through the pipelined (speculative) decode: the configuration bench.py times is the one
+compared here, bit for bit, with the CPU oracle.
+
+  * a 1 GiB / 621 k-record configs[1] batch decoded three times on one decoder: the 2nd and 3rd decode run in the steady
+    state (uniform-shape speculation, rows counted on the device, no host synchronisation) and are compared with the oracle
+    over the whole batch (the oracle is threaded over record-aligned slices);
+  * the pipelined API (tfr_decode_submit) with several batches in flight, batches released before they resolve, and every way
+    the speculation can fail (a corrupt record, a shape change, more records than provisioned, a record larger than the
+    tile slot): each must give exactly the oracle's result;
+  * configs[2] (encode, 250 k rows, byte diff) and configs[3] (SequenceExample, 100 k records) at scale;
+  * a device buffer whose allocation ends exactly at data + nbytes.
+
+Reference semantics: M/TFRecordFileReader.scala:49-81, M/TFRecordDeserializer.scala:21-35, M/TFRecordSerializer.scala:20-35."""
+import ctypes
+import threading
+
+import numpy as np
+import pytest
+
+from util import assert_columns_equal, slice_columns, record_offsets
+from spark_tfrecord_b200 import _cabi as A
+from spark_tfrecord_b200.sqltypes import *  # noqa
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def native():
+    from spark_tfrecord_b200 import _native
+    _native.lib()
+    return _native
+
+
+def oracle_check_slices(oracle, data: np.ndarray, schema, got, record_type=0, n_slices=16, what=""):
+    """threads: oracle.decode over record-aligned slices of `data`; each slice's columns == the same rows of `got`"""
+    offs = record_offsets(data)
+    n = len(offs) - 1
+    cuts = [int(round(i * n / n_slices)) for i in range(n_slices + 1)]
+    errs = []
+
+    def work(i):
+        r0, r1 = cuts[i], cuts[i + 1]
+        if r1 <= r0:
+            return
+        try:
+            want = oracle.decode(data[offs[r0]:offs[r1]], schema, record_type)
+            assert want.info["error_code"] == 0 and want.n_rows == r1 - r0, want.info
+            assert_columns_equal(slice_columns(got, r0, r1), want.columns, schema.names, f"{what} rows [{r0},{r1})")
+        except BaseException as e:      # noqa: BLE001
+            errs.append(e)
+
+    ths = [threading.Thread(target=work, args=(i,)) for i in range(n_slices)]
+    for t in ths:
+        t.start()
+    for t in ths:
+        t.join()
+    if errs:
+        raise errs[0]
+    return n
+
+
+@pytest.fixture(scope="module")
+def cfg2_gib(oracle):
+    """configs[1] at bench scale: 621,378 records = 1 GiB of framed bytes, written by the oracle's writer"""
+    from oracle.corpus import cfg2_columns
+    n = (1024 << 20) // 1728
+    sch, cols = cfg2_columns(n, seed=2024)
+    data, rc, _ = oracle.encode(cols, sch)
+    assert rc == 0
+    return sch, cols, np.frombuffer(data, dtype=np.uint8)
+
+
+def test_cfg2_one_gib_steady_state_is_bit_exact(native, oracle, cfg2_gib):
+    import torch
+    sch, cols, data = cfg2_gib
+    n = cols[0].n_rows
+    d_data = torch.from_numpy(data.copy()).cuda()
+    dec = native.Decoder(sch)
+    try:
+        for it in range(3):
+            batch, used = dec.decode(d_data)
+            assert used == len(data) and batch.info["error_code"] == 0 and batch.n_rows == n, batch.info
+            if it >= 1:
+                got = batch.to_host()
+                assert_columns_equal(got, cols, sch.names, f"decode #{it + 1} vs source")
+                assert oracle_check_slices(oracle, data, sch, got, what=f"decode #{it + 1} vs oracle") == n
+            batch.release()
+        st = dec.stats()
+        # decode #1 learns the shapes (count mode); #2 and #3 are the benchmarked mode
+        assert st["speculative_submits"] == 2 and st["speculative_redone"] == 0 and st["count_mode_batches"] == 1, st
+    finally:
+        dec.close()
+
+
+def _encode(oracle, sch, cols, record_type=0):
+    data, rc, _ = oracle.encode(cols, sch, record_type)
+    assert rc == 0
+    return np.frombuffer(data, dtype=np.uint8)
+
+
+def _check_batch(oracle, batch, data, sch, record_type=0, is_final=True, what=""):
+    want = oracle.decode(data, sch, record_type, is_final=is_final)
+    info = batch.info
+    for k in ("error_code", "error_row", "error_field", "n_rows", "consumed_bytes"):
+        assert info[k] == want.info[k], (what, k, info, want.info)
+    assert_columns_equal(batch.to_host(), want.columns, sch.names, what)
+
+
+def test_pipelined_submits_match_oracle(native, oracle):
+    """several batches in flight (more than the decoder has lanes), different sizes, one released before it resolves"""
+    import torch
+    from oracle.corpus import cfg2_columns
+    sch, _ = cfg2_columns(1, seed=1)
+    datas = [_encode(oracle, sch, cfg2_columns(nr, seed=100 + i)[1]) for i, nr in enumerate([20000, 20000, 17000, 23000, 20011, 19999, 20000, 21000])]
+    dev = [torch.from_numpy(d.copy()).cuda() for d in datas]
+    dec = native.Decoder(sch)
+    try:
+        b0, _ = dec.decode(dev[0])             # learns the shapes
+        b0.release()
+        inflight = []
+        for i in range(1, len(datas)):
+            inflight.append((i, dec.submit(dev[i])))
+            if i == 3:
+                inflight.pop()[1].release()    # dropped while pending: its lane must still be recycled correctly
+        for i, b in inflight:
+            _check_batch(oracle, b, datas[i], sch, what=f"pipelined batch {i}")
+            b.release()
+        st = dec.stats()
+        assert st["speculative_submits"] == len(datas) - 1 and st["speculative_redone"] == 0, st
+        # host input through the staging slots: the same pipeline with H2D copies on the copy stream
+        inflight = []
+        for i in range(1, 7):
+            slot = i % dec.num_staging_slots()
+            for j, b in [x for x in inflight if x[0] % dec.num_staging_slots() == slot]:
+                _check_batch(oracle, b, datas[j], sch, what=f"staged batch {j}")
+                b.release()
+                inflight.remove((j, b))
+            st_buf = dec.staging_slot(slot, len(datas[i]))
+            st_buf[: len(datas[i])] = datas[i]
+            b = dec.submit(st_buf, nbytes=len(datas[i]))
+            b.to_host_async()
+            inflight.append((i, b))
+        for j, b in inflight:
+            _check_batch(oracle, b, datas[j], sch, what=f"staged batch {j}")
+            b.release()
+        assert dec.stats()["speculative_redone"] == 0
+    finally:
+        dec.close()
+
+
+def _flip(data: np.ndarray, pos: int) -> np.ndarray:
+    out = data.copy()
+    out[pos] ^= 0x10
+    return out
+
+
+def test_speculation_failures_are_redone_exactly(native, oracle):
+    """every flag the single-pass kernel can raise leads to the oracle's result: CRC error in the middle, a length-header
+    flip, a shape change, a non-canonical record, more records than provisioned, a record larger than the slot"""
+    from oracle import pyref
+    from oracle.corpus import cfg2_columns
+    sch, cols = cfg2_columns(12000, seed=5)
+    good = _encode(oracle, sch, cols)
+    offs = record_offsets(good)
+    dec = native.Decoder(sch)
+    try:
+        for _ in range(2):
+            b, _ = dec.decode(good); b.release()
+        assert dec.stats()["speculative_submits"] == 1
+        redone = 0
+        # payload bit flip in record 7000 -> Data crc32 checking failed at row 7000, rows before delivered
+        bad = _flip(good, int(offs[7000]) + 40)
+        b = dec.submit(bad); _check_batch(oracle, b, bad, sch, what="payload flip"); assert b.info["error_code"] == A.TFR_E_CRC_DATA; b.release(); redone += 1
+        # length flip in record 300 (low byte of the length): length CRC error at that row
+        bad = _flip(good, int(offs[300]))
+        b = dec.submit(bad); _check_batch(oracle, b, bad, sch, what="length flip"); assert b.info["error_code"] == A.TFR_E_CRC_LENGTH; b.release(); redone += 1
+        # steady state again afterwards
+        b = dec.submit(good); _check_batch(oracle, b, good, sch, what="good again"); b.release()
+        assert dec.stats()["speculative_redone"] == redone
+        # shape change: FloatList[7] in one column of a second corpus -> count mode, then the new shapes are learned
+        sch2, cols2 = cfg2_columns(9000, seed=6, float_len=7)
+        other = _encode(oracle, sch2, cols2)
+        for k in range(3):
+            b = dec.submit(other); _check_batch(oracle, b, other, sch, what=f"other shapes #{k}"); b.release()
+        st = dec.stats()
+        assert st["shapes_learned"] == 2 and st["speculative_redone"] == redone + 1, st
+        redone += 1
+        # a non-canonical record (unpacked floats) among canonical ones: general path for the batch, identical rows
+        k = 4000
+        rec = bytes(other[record_offsets(other)[k] + 12: record_offsets(other)[k + 1] - 4])
+        odd = pyref.frame_fast(rec + b"\x0a\x00")           # `features` field repeated (empty): merges, not canonical
+        o2 = record_offsets(other)
+        mixed = np.concatenate([other[: o2[k]], np.frombuffer(odd, np.uint8), other[o2[k + 1]:]])
+        b = dec.submit(mixed); _check_batch(oracle, b, mixed, sch, what="non-canonical record"); b.release(); redone += 1
+        assert dec.stats()["speculative_redone"] == redone
+        # one record much larger than every slot seen so far (a long extra feature the schema ignores)
+        def ld(tag, payload):
+            return bytes([tag]) + pyref.varint(len(payload)) + payload
+        entry = ld(0x0A, ld(0x0A, b"zz") + ld(0x12, ld(0x0A, ld(0x0A, bytes(3000)))))
+        rec = bytes(other[o2[10] + 12: o2[11] - 4])
+        assert rec[0] == 0x0A and rec[1] & 0x80
+        rec2 = ld(0x0A, rec[3:] + entry)
+        wide = np.concatenate([other[: o2[10]], np.frombuffer(pyref.frame_fast(rec2), np.uint8), other[o2[11]:]])
+        for _ in range(2):
+            b = dec.submit(other); b.release()
+        before = dec.stats()["speculative_redone"]
+        b = dec.submit(wide); _check_batch(oracle, b, wide, sch, what="record larger than the slot"); b.release()
+        assert dec.stats()["speculative_redone"] == before + 1
+        b = dec.submit(wide); _check_batch(oracle, b, wide, sch, what="record larger than the slot, again"); b.release()
+    finally:
+        dec.close()
+
+
+def test_more_records_than_provisioned(native, oracle):
+    """the output capacity of a pipelined batch comes from the previous batch's record size: a block with four times as many
+    (smaller) records overflows it, is flagged on the device and redone"""
+    from spark_tfrecord_b200._cabi import HostColumn
+    sch = StructType([StructField(f"c{i}", LongType()) for i in range(8)])
+
+    def corpus(n, present, seed):
+        rng = np.random.default_rng(seed)
+        cols = []
+        for i in range(8):
+            bits = np.full(n, i < present)
+            v = rng.integers(-2**40, 2**40, n, dtype=np.int64)
+            v[~bits] = 0
+            cols.append(HostColumn(A.TFR_T_INT64, 0, n, np.packbits(bits, bitorder="little"), [], v))
+        return _encode(oracle, sch, cols)
+
+    full = corpus(40000, 8, 1)
+    thin = corpus(190000, 1, 2)
+    assert len(record_offsets(thin)) - 1 > 1.2 * (len(thin) / (len(full) / 40000))
+    dec = native.Decoder(sch)
+    try:
+        for _ in range(2):
+            b, _ = dec.decode(full); b.release()
+        assert dec.stats()["speculative_submits"] == 1
+        b = dec.submit(thin); _check_batch(oracle, b, thin, sch, what="thin records"); b.release()
+        assert dec.stats()["speculative_redone"] == 1
+        b = dec.submit(thin); _check_batch(oracle, b, thin, sch, what="thin records, capacity relearned"); b.release()
+        b = dec.submit(full); _check_batch(oracle, b, full, sch, what="back to full records"); b.release()
+        assert dec.stats()["speculative_redone"] == 1
+    finally:
+        dec.close()
+
+
+def test_nonfinal_block_with_corrupt_length_is_an_error_not_a_tail(native, oracle):
+    """a bit-flipped length that points past the block must be 'Length header crc32 checking failed' at that record, not a
+    partial record to carry over (the unverified chain of the fast path sees only the length)"""
+    from oracle.corpus import cfg2_columns
+    sch, cols = cfg2_columns(3000, seed=12)
+    good = _encode(oracle, sch, cols)
+    offs = record_offsets(good)
+    bad = good.copy()
+    bad[int(offs[2990]) + 2] ^= 0x40          # length + 4 MiB: runs past the end of the block
+    for final in (False, True):
+        dec = native.Decoder(sch)
+        try:
+            for _ in range(2):
+                b, _ = dec.decode(good); b.release()
+            b = dec.submit(bad, is_final=final)
+            _check_batch(oracle, b, bad, sch, is_final=final, what=f"corrupt length, is_final={final}")
+            assert b.info["error_code"] == A.TFR_E_CRC_LENGTH and b.info["error_row"] == 2990
+            b.release()
+            # first decode of a fresh decoder (count mode, unverified chain) as well
+            d2 = native.Decoder(sch)
+            b, used = d2.decode(bad, is_final=final)
+            _check_batch(oracle, b, bad, sch, is_final=final, what="fresh decoder")
+            b.release(); d2.close()
+        finally:
+            dec.close()
+
+
+def test_cfg3_encode_250k_rows_byte_identical(native, oracle):
+    from oracle.corpus import cfg2_columns
+    sch, cols = cfg2_columns(250_000, seed=31)
+    want, rc, _ = oracle.encode(cols, sch)
+    assert rc == 0
+    enc = native.Encoder(sch)
+    try:
+        got = enc.encode(cols)
+        assert len(got) == len(want)
+        assert got == want, "GPU encoder bytes differ from the reference writer restatement"
+        got2 = enc.encode(cols)                # second call: slot sizes learned from the first
+        assert got2 == want
+    finally:
+        enc.close()
+
+
+def test_cfg4_sequence_example_100k(native, oracle):
+    from oracle.corpus import cfg4_columns
+    sch, cols = cfg4_columns(100_000, seed=77, mean_steps=64)
+    data = _encode(oracle, sch, cols, TFR_RT_SEQUENCE_EXAMPLE)
+    dec = native.Decoder(sch, TFR_RT_SEQUENCE_EXAMPLE)
+    try:
+        for it in range(2):
+            batch, used = dec.decode(data)
+            assert used == len(data) and batch.info["error_code"] == 0 and batch.n_rows == 100_000
+            got = batch.to_host()
+            assert_columns_equal(got, cols, sch.names, f"cfg4 decode #{it + 1} vs source")
+            if it == 1:
+                oracle_check_slices(oracle, data, sch, got, record_type=TFR_RT_SEQUENCE_EXAMPLE, n_slices=8, what="cfg4 vs oracle")
+            batch.release()
+    finally:
+        dec.close()
+
+
+def test_device_buffer_ending_exactly_at_nbytes(native, oracle):
+    """data_on_device input needs no padding: cudaMalloc(nbytes) exactly, nbytes not a multiple of 16, so the 16-byte group
+    that holds the last record's tail crosses the end of the allocation.  Correctness is checked here; the absence of any
+    out-of-bounds read is what compute-sanitizer verifies on this test (profiles/r2_memcheck_exact_end.log)."""
+    import torch
+    from oracle.corpus import cfg2_columns
+    torch.cuda.init()
+    rt = ctypes.CDLL("libcudart.so.12")
+    rt.cudaMalloc.argtypes = [ctypes.POINTER(ctypes.c_void_p), ctypes.c_size_t]
+    rt.cudaMemcpy.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int]
+    rt.cudaFree.argtypes = [ctypes.c_void_p]
+    sch, cols = cfg2_columns(4099, seed=77)
+    full = _encode(oracle, sch, cols)
+    offs = record_offsets(full)
+    dec = native.Decoder(sch)
+    ptrs = []
+    tested = 0
+    try:
+        for n_rec in (4099, 4098, 4097, 4096, 4095, 4090, 33, 1):
+            data = full[: offs[n_rec]]
+            nb = len(data)
+            if nb % 16 == 0:
+                continue                      # nothing would cross the end
+            p = ctypes.c_void_p()
+            assert rt.cudaMalloc(ctypes.byref(p), nb) == 0
+            ptrs.append(p)
+            assert p.value % 16 == 0
+            assert rt.cudaMemcpy(p, data.ctypes.data, nb, 1) == 0
+            want = oracle.decode(data, sch)
+            for it in range(2):
+                batch, used = dec.decode((p.value, nb, 1))
+                assert used == nb and batch.info["error_code"] == 0 and batch.n_rows == n_rec, batch.info
+                assert_columns_equal(batch.to_host(), want.columns, sch.names, f"exact-end buffer, {n_rec} records, decode #{it + 1}")
+                batch.release()
+            tested += 1
+        assert tested >= 4
+    finally:
+        dec.close()
+        for p in ptrs:
+            rt.cudaFree(p)

@@ -35,7 +35,7 @@ def test_library_exports_every_declared_symbol(native):
     out = subprocess.run(["nm", "-D", "--defined-only", native.LIB_PATH], capture_output=True, text=True).stdout
     for s in declared:
         assert re.search(rf" T {s}\b", out), s
-    assert L.tfr_abi_version() == 1
+    assert L.tfr_abi_version() == 2
 
 
 def test_library_has_sm100a_code_only(native):

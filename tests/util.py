@@ -38,3 +38,38 @@ def assert_columns_equal(got, want, names=None, what=""):
 
 def bits(x) -> int:
     return int(np.array([x], dtype=np.float32).view(np.uint32)[0])
+
+
+def record_offsets(data) -> np.ndarray:
+    """byte offsets of the record starts of a framed buffer (+ the end of the last complete record), from the length fields"""
+    buf = np.frombuffer(data, dtype=np.uint8) if not isinstance(data, np.ndarray) else data
+    n = len(buf)
+    offs = [0]
+    pos = 0
+    while pos + 16 <= n:
+        ln = int(buf[pos:pos + 8].view("<u8")[0])
+        if pos + 16 + ln > n:
+            break
+        pos += 16 + ln
+        offs.append(pos)
+    return np.array(offs, dtype=np.int64)
+
+
+def slice_columns(cols, r0: int, r1: int):
+    """rows [r0, r1) of a list of HostColumn as new HostColumns (offsets rebased, validity re-packed)"""
+    out = []
+    for c in cols:
+        n = r1 - r0
+        if c.validity is None or len(c.validity) == 0:
+            valid = None
+        else:
+            bits = np.unpackbits(c.validity, bitorder="little")[r0:r1]
+            valid = np.packbits(bits, bitorder="little")
+        lo, hi = r0, r1
+        offs = []
+        for o in c.offsets:
+            seg = o[lo:hi + 1].astype(np.int64)
+            lo, hi = int(seg[0]), int(seg[-1])
+            offs.append((seg - seg[0]).astype(np.int32))
+        out.append(HostColumn(c.elem_type, c.depth, n, valid, offs, c.values[lo:hi]))
+    return out

@@ -1,0 +1,40 @@
+"""quick device-resident timing of the pipelined decode (developer tool; bench.py is the measurement of record)"""
+import os, sys, time
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import numpy as np
+import torch
+import bench
+from spark_tfrecord_b200 import _native
+
+mib = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
+steps = int(sys.argv[2]) if len(sys.argv) > 2 else 200
+schema, n, batches = bench.make_batches(mib, 2, seed=2024, device=0)
+dev = [torch.from_numpy(b.copy()).cuda() for b in batches]
+dec = _native.Decoder(schema)
+for i in range(4):
+    b, used = dec.decode(dev[i % 2]); assert b.info["error_code"] == 0; b.release()
+stream = torch.cuda.ExternalStream(dec.stream())
+for mode in ("submit", "decode"):
+    dec.set_profiling(True)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    e0.record(stream)
+    tot = 0
+    for i in range(steps):
+        if mode == "submit":
+            b = dec.submit(dev[i % 2])
+        else:
+            b, _ = dec.decode(dev[i % 2])
+        b.release()
+        tot += batches[i % 2].nbytes
+    e1.record(stream)
+    torch.cuda.synchronize()
+    wall = time.perf_counter() - t0
+    ms = e0.elapsed_time(e1)
+    prof = dec.get_profile()
+    print(mode, f"{tot / ms / 1e6:.1f} GB/s  {ms / steps:.4f} ms/step  wall {wall / steps * 1e3:.4f} ms/step",
+          {k: round(v / steps, 4) for k, v in prof["ms"].items()}, "launches/step", prof["launches"] / steps, dec.stats())
+    dec.set_profiling(False)
+dec.close()
