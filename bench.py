@@ -4,24 +4,28 @@
     python bench.py --gpus N --steps K --warmup W            # our arm (one process per GPU under torchrun)
     python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path on the host cores
 
-A "step" is one pass of the hot path over one batch of synthetic framed TFRecord bytes
-(Example, 32 x Int64List[1] + 16 x FloatList[8] + 16 x BytesList[1] of 16 B, entries in schema order,
-CRC verified).  Prints ONE JSON line (rank 0).
+Workload: configs[1] = 10 M unique synthetic Example records (32 x Int64List[1] + 16 x FloatList[8] + 16 x BytesList[1] of
+16 B, entries in schema order), held as a pool of 16 distinct 1 GiB batches of framed TFRecord bytes per GPU, CRC verified,
+decoded to Arrow-layout columns.  A "step" is --batches-per-step (64) batch decodes cycling through the pool = four passes
+over the 10 M records, so that the default 16 timed steps are about one second of device time.  Prints ONE JSON line (rank 0).
 
-  value  : framed input GB/s with the batches already resident in HBM (CUDA events on the decoder's
-           stream around exactly K steps, max over ranks).
-  e2e    : the same metric through the C ABI with HOST buffers: every step copies the batch from pinned
-           host memory to the device, decodes, and copies all Arrow buffers back to pinned host memory
-           (what a row-based Spark consumer needs); 3 decoder handles keep H2D / kernels / D2H overlapped.
-  roofline: the dominant kernel (decode_tile_kernel: the whole decode in one pass -- reads the framed input once,
-           writes every Arrow byte once): algorithmic bytes per launch / its mean launch time (CUDA events
-           recorded by the library around every launch in the timed region), against the measured HBM copy
-           bandwidth in MEASURED_PEAKS.json.
+  value  : framed input GB/s with the pool resident in HBM (CUDA events on the decoder's stream around exactly K steps,
+           max over ranks), through the pipelined C-ABI call tfr_decode_submit.
+  e2e    : the same metric with HOST buffers: every batch is copied from pinned host memory to the device, decoded, and
+           all Arrow buffers are copied back to pinned host memory (what a row-based Spark consumer needs), ONE decoder
+           handle on ONE thread (tfr_decode_submit + tfr_batch_to_host_async keep H2D / kernels / D2H overlapped).
+  roofline: the dominant kernel (decode_tile_kernel: the whole decode in one pass -- reads the framed input once, writes
+           every Arrow byte once): algorithmic bytes per launch / its mean launch time (CUDA events recorded by the library
+           around every launch in the timed region), against the measured HBM copy bandwidth in MEASURED_PEAKS.json.
+  parity_checked: after the timed loop one pool batch is decoded again in the very mode that was timed and compared, bit
+           for bit and over all of its records, with the CPU oracle.
   cpu_baseline: the oracle port (C restatement of the reference's per-record algorithm) on the host cores.
+  extra  : side metrics, each with its own roofline: configs[2] encode, configs[3] SequenceExample decode, configs[1]
+           with ragged bytes columns, ByteArray records.
 
 The synthetic columns are seeded numpy data; our arm frames them with the product's GPU encoder (proved byte-identical
-to the reference writer by tests/test_gpu_encode.py), the CPU arm with the oracle's writer.  Nothing under oracle/ is
-executed outside the cpu_baseline leg and the --impl reference arm.
+to the reference writer by tests/test_gpu_encode.py and tests/test_gpu_scale.py), the CPU arm with the oracle's writer.
+Nothing under oracle/ is executed outside the parity check, the cpu_baseline leg and the --impl reference arm.
 """
 from __future__ import annotations
 
@@ -32,6 +36,7 @@ import subprocess
 import sys
 import threading
 import time
+from concurrent.futures import ThreadPoolExecutor
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
@@ -41,6 +46,7 @@ import numpy as np  # noqa: E402
 
 METRIC = "TFRecord decode GB/s (1 KB Example, 64 mixed features) at 1/2/4/8 B200"
 UNIT = "GB/s"
+REC_BYTES = 1728          # mean framed record size of the configs[1] schema (measured; printed in the config)
 
 
 def parse_args():
@@ -49,11 +55,15 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=16)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch-mib", type=int, default=1024, help="framed bytes per step (approx.)")
-    ap.add_argument("--pool", type=int, default=2, help="distinct batches cycled through")
-    ap.add_argument("--cpu-sample-mib", type=int, default=48, help="framed bytes each host thread decodes per pass")
+    ap.add_argument("--batch-mib", type=int, default=1024, help="framed bytes per batch (approx.)")
+    ap.add_argument("--pool", type=int, default=16, help="distinct batches resident in HBM (16 x 1 GiB = the 10 M records of configs[1])")
+    ap.add_argument("--batches-per-step", type=int, default=64, help="batch decodes per step (cycling through the pool)")
+    ap.add_argument("--e2e-batches-per-step", type=int, default=4, help="batch decodes per step of the host-buffer (e2e) measurement")
+    ap.add_argument("--cpu-sample-mib", type=int, default=48, help="framed bytes each host thread decodes per pass (at most batch / threads)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-extra", action="store_true")
+    ap.add_argument("--no-parity", action="store_true")
     return ap.parse_args()
 
 
@@ -66,22 +76,26 @@ def dist_env():
 
 # ---------------------------------------------------------------------------------------------
 # corpus: configs[1] records.  The columns are seeded numpy data; our arm frames them with the product's own GPU encoder
-# (tests/test_gpu_encode.py proves its bytes identical to the reference writer's), the CPU arm with the oracle's writer:
-# the oracle is executed only by the CPU legs of this file.
+# (tests prove its bytes identical to the reference writer's), the CPU arm with the oracle's writer: the oracle is executed
+# only by the parity check and the CPU legs of this file.
 # ---------------------------------------------------------------------------------------------
-def cfg2_schema_and_columns(n: int, seed: int):
+def cfg2_schema():
+    from spark_tfrecord_b200.sqltypes import ArrayType, BinaryType, FloatType, LongType, StructField, StructType
+    fields = [StructField(f"i{i:02d}", LongType()) for i in range(32)]
+    fields += [StructField(f"f{i:02d}", ArrayType(FloatType())) for i in range(16)]
+    fields += [StructField(f"b{i:02d}", BinaryType()) for i in range(16)]
+    return StructType(fields)
+
+
+def cfg2_schema_and_columns(n: int, seed: int, ragged_bytes: bool = False):
     """32 x Int64List[1], 16 x FloatList[8], 16 x BytesList[1] (16 B), entries in schema order (same generator and seeds as
-    the parity tests' corpus)"""
+    the parity tests' corpus).  ragged_bytes: the bytes columns get 0..40 bytes per row instead of 16."""
     from spark_tfrecord_b200._cabi import HostColumn
-    from spark_tfrecord_b200.sqltypes import (ArrayType, BinaryType, FloatType, LongType, StructField, StructType, TFR_T_BINARY, TFR_T_FLOAT32,
-                                              TFR_T_INT64)
+    from spark_tfrecord_b200.sqltypes import TFR_T_BINARY, TFR_T_FLOAT32, TFR_T_INT64
     rng = np.random.Generator(np.random.PCG64(seed))
     valid = np.full((n + 7) // 8, 0xFF, dtype=np.uint8)
     if n % 8 and len(valid):
         valid[-1] = (1 << (n % 8)) - 1
-    fields = [StructField(f"i{i:02d}", LongType()) for i in range(32)]
-    fields += [StructField(f"f{i:02d}", ArrayType(FloatType())) for i in range(16)]
-    fields += [StructField(f"b{i:02d}", BinaryType()) for i in range(16)]
     cols = []
     for i in range(32):
         v = rng.integers(0, 2**21, n, dtype=np.int64)
@@ -97,32 +111,55 @@ def cfg2_schema_and_columns(n: int, seed: int):
         vals = rng.standard_normal(n * 8, dtype=np.float32)
         cols.append(HostColumn(TFR_T_FLOAT32, 1, n, valid, [(np.arange(n + 1, dtype=np.int64) * 8).astype(np.int32)], vals))
     for i in range(16):
-        data = rng.integers(0, 256, n * 16, dtype=np.uint8)
-        cols.append(HostColumn(TFR_T_BINARY, 0, n, valid, [(np.arange(n + 1, dtype=np.int64) * 16).astype(np.int32)], data))
-    return StructType(fields), cols
-
-
-def make_batches(batch_mib: int, pool: int, seed: int, device=None):
-    """device = a CUDA device index: framed by the product's encoder on that GPU; None: by the oracle's writer (CPU arm)"""
-    rec_bytes = 1728                      # measured mean framed record size of this schema (printed below)
-    n = max(1, (batch_mib << 20) // rec_bytes)
-    out = []
-    enc = None
-    schema = None
-    for i in range(pool):
-        schema, cols = cfg2_schema_and_columns(n, seed=seed + 1000 * i)
-        if device is None:
-            from oracle import oracle
-            data, rc, _ = oracle.encode(cols, schema)
-            assert rc == 0
+        if ragged_bytes:
+            lens = rng.integers(0, 41, n)
+            offs = np.concatenate([[0], np.cumsum(lens)]).astype(np.int32)
+            data = rng.integers(0, 256, int(offs[-1]), dtype=np.uint8)
         else:
-            from spark_tfrecord_b200 import _native
-            enc = enc or _native.Encoder(schema, 0, device)
-            data = enc.encode(cols)
+            offs = (np.arange(n + 1, dtype=np.int64) * 16).astype(np.int32)
+            data = rng.integers(0, 256, n * 16, dtype=np.uint8)
+        cols.append(HostColumn(TFR_T_BINARY, 0, n, valid, [offs], data))
+    return cfg2_schema(), cols
+
+
+def records_per_batch(batch_mib: int) -> int:
+    return max(1, (batch_mib << 20) // REC_BYTES)
+
+
+def make_host_batches(batch_mib: int, count: int, seed: int):
+    """framed by the oracle's writer (CPU arm)"""
+    from oracle import oracle
+    n = records_per_batch(batch_mib)
+    out = []
+    schema = None
+    for i in range(count):
+        schema, cols = cfg2_schema_and_columns(n, seed=seed + 1000 * i)
+        data, rc, _ = oracle.encode(cols, schema)
+        assert rc == 0
         out.append(np.frombuffer(data, dtype=np.uint8))
-    if enc is not None:
-        enc.close()
     return schema, n, out
+
+
+def make_device_pool(batch_mib: int, pool: int, seed: int, device: int, keep_host: int):
+    """`pool` distinct batches framed by the product's encoder on `device`, kept there as torch uint8 tensors; the first
+    `keep_host` are also returned as host arrays (e2e staging, CPU baseline, parity check)"""
+    import torch
+    from spark_tfrecord_b200 import _native
+    n = records_per_batch(batch_mib)
+    schema = cfg2_schema()
+    enc = _native.Encoder(schema, 0, device)
+    dev, host = [], []
+    with ThreadPoolExecutor(max_workers=min(4, pool)) as ex:       # numpy's generators release the GIL while they fill
+        futs = [ex.submit(cfg2_schema_and_columns, n, seed + 1000 * i) for i in range(pool)]
+        for i, f in enumerate(futs):
+            _, cols = f.result()
+            data = np.frombuffer(enc.encode(cols), dtype=np.uint8)
+            dev.append(torch.from_numpy(data.copy()).cuda(device))
+            if i < keep_host:
+                host.append(data)
+            del cols
+    enc.close()
+    return schema, n, dev, host
 
 
 def host_mem_available():
@@ -168,36 +205,77 @@ def host_cores():
     return n
 
 
+def bind_to_gpu_numa_node(index: int):
+    """Pin this rank (and the pinned buffers it allocates from now on: first touch) to the CPUs next to its GPU.  Returns a
+    description for the JSON line; never fails the run."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        idx = int(vis.split(",")[index]) if vis and vis.split(",")[index].isdigit() else index
+        h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        near = {64 * w + b for w, word in enumerate(words) for b in range(64) if (word >> b) & 1}
+        cur = os.sched_getaffinity(0)
+        want = near & cur
+        if not want:
+            return {"bound": False, "why": "GPU-local CPUs are outside this process's cpuset"}
+        if want != cur:
+            os.sched_setaffinity(0, want)
+        node = None
+        try:
+            for d in sorted(os.listdir("/sys/devices/system/node")):
+                if d.startswith("node") and d[4:].isdigit():
+                    cpus = set()
+                    for part in open(f"/sys/devices/system/node/{d}/cpulist").read().strip().split(","):
+                        lo, _, hi = part.partition("-")
+                        cpus.update(range(int(lo), int(hi or lo) + 1))
+                    if want <= cpus:
+                        node = int(d[4:])
+                        break
+        except Exception:
+            pass
+        return {"bound": True, "cpus": len(want), "numa_node": node}
+    except Exception as e:      # noqa: BLE001
+        return {"bound": False, "why": f"{type(e).__name__}: {e}"[:120]}
+
+
 # ---------------------------------------------------------------------------------------------
 # CPU arm: the oracle port on all host cores
 # ---------------------------------------------------------------------------------------------
-def record_aligned_slices(batch: np.ndarray, n_slices: int, slice_bytes: int):
-    """[(start, end)] of record-aligned windows spread over the batch"""
-    import struct
+def record_starts(batch: np.ndarray) -> np.ndarray:
     offs = [0]
     pos = 0
     n = len(batch)
-    mv = batch
-    while pos + 12 <= n:
-        ln = int.from_bytes(mv[pos:pos + 8].tobytes(), "little")
+    while pos + 16 <= n:
+        ln = int(batch[pos:pos + 8].view("<u8")[0])
+        if pos + 16 + ln > n:
+            break
         pos += 16 + ln
         offs.append(pos)
-    offs = np.array(offs[:-1] if offs[-1] > n else offs)
+    return np.array(offs, dtype=np.int64)
+
+
+def record_aligned_slices(batch: np.ndarray, n_slices: int, slice_bytes: int, offs=None):
+    """[(start, end)] of disjoint record-aligned windows spread evenly over the batch"""
+    offs = record_starts(batch) if offs is None else offs
+    n = int(offs[-1])
+    slice_bytes = min(slice_bytes, n // max(1, n_slices))
     out = []
     for i in range(n_slices):
-        start_target = (i * max(1, (n - slice_bytes)) // max(1, n_slices)) if n > slice_bytes else 0
-        si = int(np.searchsorted(offs, start_target))
+        lo = i * n // n_slices
+        si = int(np.searchsorted(offs, lo))
         s = int(offs[min(si, len(offs) - 1)])
         ei = int(np.searchsorted(offs, min(n, s + slice_bytes), side="right")) - 1
         e = int(offs[max(ei, si)])
-        if e <= s:
-            s, e = 0, int(offs[-1])
-        out.append((s, e))
+        if e > s:
+            out.append((s, e))
     return out
 
 
-def cpu_pass(schema, batch, slices, threads):
-    """every thread decodes its slice with the oracle; returns (bytes, seconds)"""
+def cpu_pass(schema, batch, slices):
+    """one thread per slice decodes it with the oracle; returns (bytes, seconds)"""
     from oracle import oracle
     oracle.lib()
     errs = []
@@ -208,7 +286,7 @@ def cpu_pass(schema, batch, slices, threads):
         if r.info["error_code"] != 0:
             errs.append(r.info)
 
-    ths = [threading.Thread(target=work, args=(i,)) for i in range(threads)]
+    ths = [threading.Thread(target=work, args=(i,)) for i in range(len(slices))]
     t0 = time.perf_counter()
     for t in ths:
         t.start()
@@ -216,7 +294,20 @@ def cpu_pass(schema, batch, slices, threads):
         t.join()
     dt = time.perf_counter() - t0
     assert not errs, errs
-    return sum(e - s for s, e in slices[:threads]), dt
+    return sum(e - s for s, e in slices), dt
+
+
+def workload_config(args, n_records, batch_bytes, extra=None):
+    c = {"workload": "configs[1]: Example decode, 32xInt64List[1] + 16xFloatList[8] + 16xBytesList[1](16 B), CRC verified, -> Arrow columns",
+         "batch_mib": args.batch_mib, "records_per_batch": n_records, "framed_bytes_per_batch": batch_bytes,
+         "mean_framed_record_bytes": round(batch_bytes / max(1, n_records), 1),
+         "pool_batches": args.pool, "unique_records": n_records * args.pool,
+         "batches_per_step": args.batches_per_step, "records_per_step": n_records * args.batches_per_step,
+         "framed_bytes_per_step": batch_bytes * args.batches_per_step,
+         "l2": "every batch (1 GiB) is 8x the 126 MB L2 and consecutive decodes take different batches of a 16 GiB pool"}
+    if extra:
+        c.update(extra)
+    return c
 
 
 def run_reference(args):
@@ -224,15 +315,15 @@ def run_reference(args):
     if rank != 0:
         return
     cores = host_cores()
-    sample = args.cpu_sample_mib << 20
-    schema, n, batches = make_batches(max(64, min(args.batch_mib, 256)), 1, seed=2024)
+    schema, n, batches = make_host_batches(args.batch_mib, 1, seed=2024)
     batch = batches[0]
-    slices = record_aligned_slices(batch, cores, sample)
+    slices = record_aligned_slices(batch, cores, args.cpu_sample_mib << 20)
+    per_pass = sum(e - s for s, e in slices)
     for _ in range(args.warmup):
-        cpu_pass(schema, batch, slices, cores)
+        cpu_pass(schema, batch, slices)
     tot_b, tot_t = 0, 0.0
     for _ in range(args.steps):
-        b, dt = cpu_pass(schema, batch, slices, cores)
+        b, dt = cpu_pass(schema, batch, slices)
         tot_b += b
         tot_t += dt
     v = tot_b / tot_t / 1e9
@@ -240,31 +331,22 @@ def run_reference(args):
         "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * tot_t / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u8", "data": "synthetic", "impl": "reference",
-        "config": workload_config(args, n, int(len(batch)), extra={"arm": "CPU port of the reference path (oracle/tfr_oracle.c); the JVM reference cannot run here (no JDK)"}),
+        "config": workload_config(args, n, int(len(batch))),
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": f"{cores} threads x {sample >> 20} MiB record-aligned slices of one batch per step"},
+                         "sample": f"each step = {cores} threads x one disjoint record-aligned slice ({per_pass >> 20} MiB in total) of one configs[1] batch "
+                                   "of the same size as the GPU arm's; oracle/tfr_oracle.c, the C port of the reference path (the JVM reference cannot run "
+                                   "here: no JDK)"},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line))
 
 
-def workload_config(args, n_records, batch_bytes, extra=None):
-    c = {"workload": "configs[1]: Example decode, 32xInt64List[1] + 16xFloatList[8] + 16xBytesList[1](16 B), CRC verified, -> Arrow columns",
-         "records_per_step": n_records, "framed_bytes_per_step": batch_bytes,
-         "mean_framed_record_bytes": round(batch_bytes / max(1, n_records), 1),
-         "l2": "each step's input (1 GiB by default, never below 128 MiB) is larger than the 126 MB L2; batches cycle through a pool",
-         "pool_batches": args.pool}
-    if extra:
-        c.update(extra)
-    return c
-
-
 # ---------------------------------------------------------------------------------------------
 # clocks
 # ---------------------------------------------------------------------------------------------
 class ClockSampler:
-    """SM clock + throttle reasons sampled with NVML every ~2 ms DURING the timed regions (resident + e2e);
+    """SM clock + throttle reasons sampled with NVML DURING the timed regions (resident + e2e);
     falls back to `nvidia-smi -lms` when pynvml is unavailable."""
     REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
@@ -341,13 +423,180 @@ class ClockSampler:
 
 
 # ---------------------------------------------------------------------------------------------
+# parity inside the bench: the timed mode, one whole batch, bit for bit against the oracle
+# ---------------------------------------------------------------------------------------------
+def parity_check(dec, schema, d_batch, h_batch, threads):
+    """decode d_batch exactly as the timed loop does (pipelined submit in steady state) and compare every record with
+    the oracle's decode of the same bytes (threads over record-aligned slices)"""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from oracle import oracle
+    from util import assert_columns_equal, slice_columns
+    s0 = dec.stats()
+    b = dec.submit(d_batch)
+    got = b.to_host()
+    info = dict(b.info)
+    b.release()
+    s1 = dec.stats()
+    speculative = s1["speculative_submits"] == s0["speculative_submits"] + 1 and s1["speculative_redone"] == s0["speculative_redone"]
+    offs = record_starts(h_batch)
+    n = len(offs) - 1
+    assert info["error_code"] == 0 and info["n_rows"] == n, info
+    cuts = [int(round(i * n / threads)) for i in range(threads + 1)]
+    errs = []
+
+    def work(i):
+        r0, r1 = cuts[i], cuts[i + 1]
+        if r1 <= r0:
+            return
+        try:
+            want = oracle.decode(h_batch[offs[r0]:offs[r1]], schema)
+            assert want.info["error_code"] == 0 and want.n_rows == r1 - r0
+            assert_columns_equal(slice_columns(got, r0, r1), want.columns, schema.names, f"bench parity rows [{r0},{r1})")
+        except BaseException as e:      # noqa: BLE001
+            errs.append(e)
+
+    ths = [threading.Thread(target=work, args=(i,)) for i in range(threads)]
+    for t in ths:
+        t.start()
+    for t in ths:
+        t.join()
+    if errs:
+        raise errs[0]
+    return {"records": n, "columns": len(got), "bit_exact": True,
+            "mode": "steady state: uniform-shape speculation, rows counted on the device, pipelined submit" if speculative else "synchronising path",
+            "against": "oracle/tfr_oracle.c over the whole batch (record-aligned slices, one host thread each)"}
+
+
+# ---------------------------------------------------------------------------------------------
+# side metrics (rank 0, N = 1): each a short resident loop with its own roofline
+# ---------------------------------------------------------------------------------------------
+def _roof(alg_bytes, ms, peak):
+    a = alg_bytes / (ms * 1e-3) / 1e9 if ms > 0 else 0.0
+    return {"bound": "hbm", "achieved": a, "peak": peak, "unit": "GB/s", "frac": a / peak}
+
+
+def _time_decoder(torch, dec, d_batches, reps):
+    stream = torch.cuda.ExternalStream(dec.stream())
+    for i in range(3):
+        b, _ = dec.decode(d_batches[i % len(d_batches)])
+        assert b.info["error_code"] == 0, b.info
+        out_bytes, n_rows = b.info["out_bytes"], b.info["n_rows"]
+        b.release()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    tot = 0
+    for i in range(reps):
+        b = dec.submit(d_batches[i % len(d_batches)])
+        b.release()
+        tot += d_batches[i % len(d_batches)].numel()
+    e1.record(stream)
+    torch.cuda.synchronize()
+    return tot, e0.elapsed_time(e1), out_bytes, n_rows
+
+
+def run_extras(torch, dev, peak):
+    from spark_tfrecord_b200 import _native
+    from spark_tfrecord_b200._cabi import HostColumn, tfr_column
+    from spark_tfrecord_b200.sqltypes import (ArrayType, FloatType, LongType, StructField, StructType, TFR_T_FLOAT32, TFR_T_INT64,
+                                              byte_array_schema, TFR_T_BINARY)
+    out = {}
+    n = records_per_batch(256)
+
+    # ---- configs[2]: encode, columns resident in HBM -> framed bytes ----
+    schema, cols = cfg2_schema_and_columns(n, seed=4242)
+    keep, dcols = [], []
+    for c in cols:
+        t = tfr_column()
+        hc = c.to_ctypes()
+        for f, _ in tfr_column._fields_:
+            setattr(t, f, getattr(hc, f))
+        v = torch.from_numpy(c.validity).cuda(dev); keep.append(v); t.validity = v.data_ptr()
+        for l, o in enumerate(c.offsets):
+            ot = torch.from_numpy(o).cuda(dev); keep.append(ot); t.offsets[l] = ot.data_ptr()
+        vt = torch.from_numpy(c.values.view(np.uint8)).cuda(dev); keep.append(vt); t.values = vt.data_ptr()
+        dcols.append(t)
+    enc = _native.Encoder(schema, 0, dev)
+    stream = torch.cuda.ExternalStream(enc.stream())
+    for _ in range(3):
+        _, nb = enc.encode_columns(dcols, True)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 12
+    e0.record(stream)
+    for _ in range(reps):
+        enc.encode_columns(dcols, True)
+    e1.record(stream)
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    in_bytes = sum(c.nbytes() for c in cols)
+    framed = np.frombuffer(enc.result_host(), dtype=np.uint8)
+    out["cfg3_encode"] = {"workload": f"configs[2]: {n} rows x 64 columns resident in HBM -> framed TFRecord bytes (CRC framed, byte-identical to the reference writer)",
+                          "value": nb / (ms * 1e-3) / 1e9, "unit": "GB/s of framed output", "ms_per_batch": ms,
+                          "roofline": dict(_roof(in_bytes + nb, ms, peak), algorithmic_bytes=in_bytes + nb,
+                                           note="whole encode call (size pass + scan + emit + the call's host synchronisation) against columns read once + framed bytes written once")}
+    enc.close()
+    del keep, dcols
+
+    # ---- configs[1] with ragged bytes columns (0..40 B): count mode + pass 2 ----
+    schema_r, cols_r = cfg2_schema_and_columns(n, seed=777, ragged_bytes=True)
+    enc = _native.Encoder(schema_r, 0, dev)
+    d_r = [torch.from_numpy(np.frombuffer(enc.encode(cols_r), dtype=np.uint8).copy()).cuda(dev)]
+    enc.close()
+    dec = _native.Decoder(schema_r, 0, dev)
+    tot, ms, ob, nr = _time_decoder(torch, dec, d_r, 12)
+    out["cfg2_ragged_bytes"] = {"workload": f"configs[1] with BytesList values of 0..40 bytes ({nr} records per batch): variable-width columns are not uniform",
+                                "value": tot / ms / 1e6, "unit": UNIT, "ms_per_batch": ms / 12, "stats": dec.stats(),
+                                "roofline": dict(_roof(d_r[0].numel() + ob, ms / 12, peak), algorithmic_bytes=d_r[0].numel() + ob, note="whole step (frame index + tile kernel + scans + pass 2)")}
+    dec.close()
+
+    # ---- configs[3]: SequenceExample, FeatureList of FloatList (ragged, mean 64 steps) ----
+    rng = np.random.Generator(np.random.PCG64(77))
+    ns = 120_000
+    steps = rng.poisson(64, ns).astype(np.int64)
+    o0 = np.concatenate([[0], np.cumsum(steps)]).astype(np.int32)
+    inner = rng.integers(1, 9, int(o0[-1])).astype(np.int64)
+    o1 = np.concatenate([[0], np.cumsum(inner)]).astype(np.int32)
+    valid = np.full((ns + 7) // 8, 0xFF, dtype=np.uint8)
+    sch4 = StructType([StructField("id", LongType()), StructField("seq", ArrayType(ArrayType(FloatType())))])
+    cols4 = [HostColumn(TFR_T_INT64, 0, ns, valid, [], rng.integers(0, 2**40, ns, dtype=np.int64)),
+             HostColumn(TFR_T_FLOAT32, 2, ns, valid, [o0, o1], rng.standard_normal(int(o1[-1]), dtype=np.float32))]
+    enc = _native.Encoder(sch4, 1, dev)
+    d_4 = [torch.from_numpy(np.frombuffer(enc.encode(cols4), dtype=np.uint8).copy()).cuda(dev)]
+    enc.close()
+    dec = _native.Decoder(sch4, 1, dev)
+    tot, ms, ob, nr = _time_decoder(torch, dec, d_4, 12)
+    out["cfg4_sequence_example"] = {"workload": f"configs[3]: {nr} SequenceExample records, FeatureList of FloatList[1..8], Poisson(64) steps -> list<list<float32>>",
+                                    "value": tot / ms / 1e6, "unit": UNIT, "ms_per_batch": ms / 12,
+                                    "roofline": dict(_roof(d_4[0].numel() + ob, ms / 12, peak), algorithmic_bytes=d_4[0].numel() + ob, note="whole step")}
+    dec.close()
+
+    # ---- ByteArray records (1 KiB payloads): framing + CRC only ----
+    nb_rec = 200_000
+    payload = rng.integers(0, 256, nb_rec * 1024, dtype=np.uint8)
+    schb = byte_array_schema()
+    colsb = [HostColumn(TFR_T_BINARY, 0, nb_rec, np.full((nb_rec + 7) // 8, 0xFF, np.uint8), [(np.arange(nb_rec + 1, dtype=np.int64) * 1024).astype(np.int32)], payload)]
+    enc = _native.Encoder(schb, 2, dev)
+    d_b = [torch.from_numpy(np.frombuffer(enc.encode(colsb), dtype=np.uint8).copy()).cuda(dev)]
+    enc.close()
+    dec = _native.Decoder(schb, 2, dev)
+    tot, ms, ob, nr = _time_decoder(torch, dec, d_b, 12)
+    out["byte_array"] = {"workload": f"recordType=ByteArray: {nr} records of 1 KiB, CRC verified -> one binary column",
+                         "value": tot / ms / 1e6, "unit": UNIT, "ms_per_batch": ms / 12,
+                         "roofline": dict(_roof(d_b[0].numel() + ob, ms / 12, peak), algorithmic_bytes=d_b[0].numel() + ob, note="whole step")}
+    dec.close()
+    return out
+
+
+# ---------------------------------------------------------------------------------------------
 # our arm
 # ---------------------------------------------------------------------------------------------
 def run_ours(args):
+    rank, world, local = dist_env()
+    numa = bind_to_gpu_numa_node(local)       # before CUDA and any pinned allocation
     import torch
     from spark_tfrecord_b200 import _native
     _native.lib()      # fails loudly when libtfrgpu.so is missing
-    rank, world, local = dist_env()
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; there is no CPU fallback for the product path")
     torch.cuda.set_device(local)
@@ -362,28 +611,42 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    # host footprint per rank is about 9x the batch (pool copies, pinned staging and pinned Arrow buffers of the three
-    # e2e handles): keep the default batch only if 8 ranks of it fit the host (the same decision at every N, so the
+    # host footprint per rank: 3 host batches + 3 pinned staging slots + 3 pinned Arrow buffers + the generator's columns:
+    # about 12x the batch.  Keep the default batch only if 8 ranks of it fit the host (the same decision at every N, so the
     # per-GPU work does not change with the number of ranks)
-    batch_mib, reduced = args.batch_mib, False
+    reduced = False
     avail = host_mem_available()
-    while avail is not None and batch_mib > 128 and 8 * 10 * (batch_mib << 20) > avail:
-        batch_mib //= 2
+    while avail is not None and args.batch_mib > 128 and 8 * 12 * (args.batch_mib << 20) > avail:
+        args.batch_mib //= 2
         reduced = True
-    schema, n_rec, batches = make_batches(batch_mib, args.pool, seed=2024 + 7919 * rank, device=dev)
-    batch_bytes = [int(b.nbytes) for b in batches]
-    d_batches = [torch.from_numpy(b.copy()).cuda(dev) for b in batches]
+    schema, n_rec, d_batches, h_batches = make_device_pool(args.batch_mib, args.pool, seed=2024 + 7919 * rank, device=dev, keep_host=3)
+    batch_bytes = [int(b.numel()) for b in d_batches]
+    P = len(d_batches)
 
     # ---------------- resident path: the metric ----------------
     dec = _native.Decoder(schema, 0, dev)
     stream = torch.cuda.ExternalStream(dec.stream(), device=dev)
     out_bytes = 0
-    for i in range(args.warmup):
-        b, used = dec.decode(d_batches[i % len(d_batches)])
-        assert used == batch_bytes[i % len(d_batches)] and b.info["error_code"] == 0, b.info
-        b.wait()
+    for i in range(3):                         # the decoder learns record size and column shapes
+        b, used = dec.decode(d_batches[i % P])
+        assert used == batch_bytes[i % P] and b.info["error_code"] == 0, b.info
         out_bytes = b.info["out_bytes"]
         b.release()
+
+    def resident_steps(steps, k0=0):
+        nb = 0
+        k = k0
+        for _ in range(steps):
+            for _ in range(args.batches_per_step):
+                b = dec.submit(d_batches[k % P])
+                b.release()                   # the work stays enqueued; the lane is recycled when its kernels are done
+                nb += batch_bytes[k % P]
+                k += 1
+        return nb, k
+
+    _, k = resident_steps(args.warmup)
+    torch.cuda.synchronize()
+    stats0 = dec.stats()
     dec.set_profiling(True)
     clocks = ClockSampler(dev)
     barrier()
@@ -391,61 +654,72 @@ def run_ours(args):
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t_wall0 = time.perf_counter()
     ev0.record(stream)
-    in_bytes = 0
-    for i in range(args.steps):
-        k = i % len(d_batches)
-        b, used = dec.decode(d_batches[k])
-        b.release()                       # stream-ordered frees; the work itself stays enqueued
-        in_bytes += used
+    in_bytes, k = resident_steps(args.steps, k)
     ev1.record(stream)
     barrier()
     t_wall = time.perf_counter() - t_wall0
     ms = ev0.elapsed_time(ev1)
     prof = dec.get_profile()
     dec.set_profiling(False)
+    stats1 = dec.stats()
+    n_timed = args.steps * args.batches_per_step
+    timed_stats = {k2: stats1[k2] - stats0[k2] for k2 in stats1}
+    # every timed decode ran in the pipelined single-pass mode and none was flagged (a flagged batch would have been redone)
+    assert timed_stats["speculative_submits"] == n_timed and timed_stats["speculative_redone"] == 0, timed_stats
 
-    # ---------------- end to end: pinned host -> device -> pinned host ----------------
+    # ---------------- parity of the timed mode, whole batch ----------------
+    parity = None
+    if not args.no_parity and rank == 0:
+        parity = parity_check(dec, schema, d_batches[0], h_batches[0], max(1, host_cores()))
+
+    # ---------------- end to end: pinned host -> device -> pinned host, one handle, one thread ----------------
     e2e = None
     if not args.no_e2e:
-        n_workers = int(os.environ.get("TFR_E2E_WORKERS", "3"))
-        decs = [_native.Decoder(schema, 0, dev) for _ in range(n_workers)]
+        d2 = _native.Decoder(schema, 0, dev)
+        S = d2.num_staging_slots()
         stages = []
-        for w, d in enumerate(decs):
-            src = batches[w % len(batches)]
-            st = d.staging(src.nbytes)
-            st[: src.nbytes] = src          # the JVM side writes file bytes here; not part of the timed region
+        for s in range(S):
+            src = h_batches[s % len(h_batches)]
+            st = d2.staging_slot(s, src.nbytes)
+            st[: src.nbytes] = src            # the JVM side writes file bytes here; not part of the timed region
             stages.append((st, src.nbytes))
+        for i in range(3):
+            b, used = d2.decode(stages[0][0], nbytes=stages[0][1])
+            b.to_host_raw()
+            b.release()
         d2h = [0]
 
-        def e2e_steps(steps, w):
-            d = decs[w]
-            st, nb = stages[w]
-            for i in range(w, steps, n_workers):
-                b, used = d.decode(st, nbytes=nb)          # H2D from pinned memory + kernels
-                cols = b.to_host_raw()                     # D2H of every Arrow buffer into pinned memory
-                assert b.info["error_code"] == 0 and used == nb
-                if i == w:
-                    d2h[0] = b.info["out_bytes"]
-                b.release()
+        def e2e_batches(count):
+            inflight = [None] * S
+            tot = 0
+            for i in range(count):
+                s = i % S
+                if inflight[s] is not None:                 # the slot's previous batch: its Arrow buffers are on the host now
+                    ob = inflight[s]
+                    ob.to_host_raw()
+                    assert ob.info["error_code"] == 0 and ob.info["consumed_bytes"] == stages[s][1]
+                    d2h[0] = ob.info["out_bytes"]
+                    ob.release()
+                b = d2.submit(stages[s][0], nbytes=stages[s][1])   # H2D from pinned memory + kernels, no host sync
+                b.to_host_async()                                  # D2H of every Arrow buffer into pinned memory, behind the kernels
+                inflight[s] = b
+                tot += stages[s][1]
+            for ob in inflight:
+                if ob is not None:
+                    ob.to_host_raw()
+                    assert ob.info["error_code"] == 0
+                    ob.release()
+            return tot
 
-        def run_e2e(steps):
-            ths = [threading.Thread(target=e2e_steps, args=(steps, w)) for w in range(n_workers)]
-            for t in ths:
-                t.start()
-            for t in ths:
-                t.join()
-
-        run_e2e(max(args.warmup, n_workers))
+        e2e_batches(max(2 * S, args.warmup))
         barrier()
         t0 = time.perf_counter()
-        run_e2e(args.steps)
+        e2e_bytes = e2e_batches(args.steps * args.e2e_batches_per_step)
         torch.cuda.synchronize()
         barrier()
         t_e2e = time.perf_counter() - t0
-        e2e_bytes = sum(stages[i % n_workers][1] for i in range(args.steps))
-        e2e = (e2e_bytes, t_e2e, d2h[0])
-        for d in decs:
-            d.close()
+        e2e = (e2e_bytes, t_e2e, d2h[0], d2.stats())
+        d2.close()
 
     clk = clocks.stop()
 
@@ -475,67 +749,78 @@ def run_ours(args):
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
-    n_fix = 32
-    single_pass = prof["ms"]["pass2"] == 0.0            # tile fast path with uniform-shape speculation: one kernel reads the input and writes every Arrow byte
-    if single_pass:
-        kernel_name = "decode_tile_kernel"
-        p1_alg = batch_bytes[0] + int(out_bytes)        # framed input read once + Arrow output written once (algorithmic bytes of the whole decode)
-    else:
-        kernel_name = "decode_pass1_kernel / decode_tile_kernel (count mode)"
-        p1_alg = batch_bytes[0] + n_rec * n_fix * 8     # framed input + the fixed-width values this kernel writes
+    p1_alg = batch_bytes[0] + int(out_bytes)        # framed input read once + Arrow output written once (algorithmic bytes of the whole decode of one batch)
     p1_ms = prof["ms"]["pass1"] / max(1, prof["pass1_launches"])
     achieved = p1_alg / (p1_ms * 1e-3) / 1e9 if p1_ms > 0 else 0.0
-    stage_ms = {k: round(v / args.steps, 4) for k, v in prof["ms"].items()}
-    step_alg = batch_bytes[0] + out_bytes
+    ms_per_batch = ms / n_timed
+    stage_ms = {k2: round(v / n_timed, 4) for k2, v in prof["ms"].items()}
     traffic = None
     traffic_src = None
     try:
-        with open(os.path.join(ROOT, "profiles", "r1_tile_traffic.json")) as f:
+        with open(os.path.join(ROOT, "profiles", "tile_traffic.json")) as f:
             tj = json.load(f)
-        if single_pass:
-            traffic = int(tj["dram_bytes_per_framed_byte"] * batch_bytes[0])
-            traffic_src = f"ncu dram__bytes_read+write per framed byte ({tj['source']}) x this batch"
+        traffic = int(tj["dram_bytes_per_framed_byte"] * batch_bytes[0])
+        traffic_src = f"ncu dram__bytes_read+write per framed byte of this kernel ({tj['source']}) x this batch; not re-measured by this run"
     except Exception:
         pass
-    roof = {"bound": "hbm", "kernel": kernel_name, "achieved": achieved, "peak": peak, "unit": "GB/s",
+    roof = {"bound": "hbm", "kernel": "decode_tile_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
             "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
-            "algorithmic_bytes_per_launch": p1_alg, "kernel_ms_per_launch": p1_ms,
-            "share_of_step": p1_ms / (ms / args.steps) if ms > 0 else None}
+            "algorithmic_bytes_per_launch": p1_alg, "kernel_ms_per_launch": p1_ms, "launches_timed": int(prof["pass1_launches"]),
+            "share_of_step": p1_ms / ms_per_batch if ms > 0 else None,
+            "note": "launch time measured live with CUDA events while the next batch's frame index runs concurrently on a second stream"}
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u8", "data": "synthetic",
         "config": workload_config(args, n_rec, batch_bytes[0], extra={
-            "arrow_out_bytes_per_step": int(out_bytes),
-            "timing": "CUDA events on the decoder stream (value); wall clock around pipelined steps incl. copies (e2e); max over ranks",
+            "arrow_out_bytes_per_batch": int(out_bytes),
+            "timing": "CUDA events on the decoder's stream around K steps (value); wall clock around the pipelined host-buffer loop incl. copies (e2e); max over ranks",
             "parallelism": f"file/block sharded, {world} rank(s), no collective on the data path",
-            "batch_mib": batch_mib, "batch_reduced_for_host_memory": reduced}),
+            "batch_reduced_for_host_memory": reduced, "numa": numa}),
+        "ms_per_batch": ms_per_batch,
         "roofline": roof,
-        "step_hbm": {"algorithmic_bytes_per_step": int(step_alg), "achieved_GBps": step_alg / (ms / args.steps * 1e-3) / 1e9,
-                     "frac_of_peak": step_alg / (ms / args.steps * 1e-3) / 1e9 / peak, "stage_ms_per_step": stage_ms},
+        "step_hbm": {"algorithmic_bytes_per_batch": int(p1_alg), "achieved_GBps": p1_alg / (ms_per_batch * 1e-3) / 1e9,
+                     "frac_of_peak": p1_alg / (ms_per_batch * 1e-3) / 1e9 / peak, "stage_ms_per_batch": stage_ms,
+                     "note": "stages overlap: the frame index (and the uniform columns' offsets) of batch t+1 run on a second stream under the tile kernel of batch t"},
+        "pipeline": dict(timed_stats, host_syncs_per_batch=0),
         "clocks": clk,
         "gpu_launches": int(prof["launches"]),
         "wall_s_timed_region": t_wall,
     }
+    if parity:
+        line["parity_checked"] = parity
     if e2e:
-        line["e2e"] = {"value": tot_e2e / t_e2e_max / 1e9, "unit": UNIT, "h2d_bytes_per_step": int(batch_bytes[0]),
-                       "d2h_bytes_per_step": int(e2e[2]), "pipeline": f"{n_workers} decoder handles (threads), pinned staging in, pinned Arrow buffers out"}
+        eb = args.e2e_batches_per_step
+        line["e2e"] = {"value": tot_e2e / t_e2e_max / 1e9, "unit": UNIT, "h2d_bytes_per_step": int(batch_bytes[0]) * eb,
+                       "d2h_bytes_per_step": int(e2e[2]) * eb, "batches_per_step": eb, "steps": args.steps,
+                       "pipeline": "ONE decoder handle on ONE thread: tfr_decode_submit (H2D on the copy stream, frame index, tile kernel) + "
+                                   "tfr_batch_to_host_async (D2H on the copy-out stream), 3 pinned staging slots in, pinned Arrow buffers out",
+                       "stats": e2e[3]}
     # ---------------- CPU baseline beside it (rank 0, N=1 only) ----------------
     if not args.no_cpu and world == 1:
         cores = host_cores()
-        sample = args.cpu_sample_mib << 20
-        slices = record_aligned_slices(batches[0], cores, sample)
-        cpu_pass(schema, batches[0], slices, cores)
+        slices = record_aligned_slices(h_batches[0], cores, args.cpu_sample_mib << 20)
+        cpu_pass(schema, h_batches[0], slices)
         tb, tt, passes = 0, 0.0, 0
         while tt < 8.0 and passes < 40:
-            bb, dt = cpu_pass(schema, batches[0], slices, cores)
+            bb, dt = cpu_pass(schema, h_batches[0], slices)
             tb += bb
             tt += dt
             passes += 1
         line["cpu_baseline"] = {"value": tb / tt / 1e9, "unit": UNIT, "cores": cores, "kind": "port",
-                                "sample": f"{cores} threads x {sample >> 20} MiB record-aligned slices, {tt:.1f} s of wall time"}
+                                "sample": f"{cores} threads x one disjoint record-aligned slice of one batch ({sum(e - s for s, e in slices) >> 20} MiB per pass), {passes} passes, {tt:.1f} s of wall time"}
+    if not args.no_extra and world == 1:
+        try:
+            dec.close()
+            dec = None
+            del d_batches
+            torch.cuda.empty_cache()
+            line["extra"] = run_extras(torch, dev, peak)
+        except Exception as e:      # noqa: BLE001  (side metrics never fail the headline)
+            line["extra"] = {"error": f"{type(e).__name__}: {e}"[:300]}
     print(json.dumps(line))
-    dec.close()
+    if dec is not None:
+        dec.close()
     if use_dist:
         dist.destroy_process_group()
 

@@ -47,26 +47,47 @@ struct PinnedPool {
   void release_all() { for (auto& b : blocks) cudaFreeHost(b.p); blocks.clear(); }
 };
 
-// device blocks reused across batches (all use is ordered on the owning decoder's stream)
+// device blocks reused across batches.  A block goes back to the pool when its batch is released, possibly while kernels that
+// write it are still queued on the decode stream: `ready` is recorded there at that moment, and whoever takes the block for
+// work on ANOTHER stream waits for it.  Free blocks are handed out oldest-release-first, so that in a steady pipeline the
+// block a new batch gets was released two or three batches ago and its event has long fired.
 struct DevPool {
-  struct Block { void* p; size_t cap; bool used; };
+  struct Block { void* p; size_t cap; bool used; cudaEvent_t ready; unsigned long long stamp; };
   std::vector<Block> blocks;
-  void* acquire(size_t bytes) {
+  unsigned long long clock = 0;
+  void* acquire(size_t bytes, cudaEvent_t* ready_out = nullptr) {
     int best = -1;
-    for (size_t i = 0; i < blocks.size(); ++i)
-      if (!blocks[i].used && blocks[i].cap >= bytes && (best < 0 || blocks[i].cap < blocks[best].cap)) best = (int)i;
-    if (best >= 0) { blocks[best].used = true; return blocks[best].p; }
+    for (size_t i = 0; i < blocks.size(); ++i) {
+      const Block& b = blocks[i];
+      if (b.used || b.cap < bytes) continue;
+      if (best < 0) { best = (int)i; continue; }
+      const Block& c = blocks[best];
+      // a block up to 1/8 larger than the smallest fit counts as the same size class: among those, the oldest release wins
+      const bool same_class = b.cap <= c.cap + c.cap / 8 && c.cap <= b.cap + b.cap / 8;
+      if (same_class ? b.stamp < c.stamp : b.cap < c.cap) best = (int)i;
+    }
+    if (best >= 0) { blocks[best].used = true; if (ready_out) *ready_out = blocks[best].stamp ? blocks[best].ready : nullptr; return blocks[best].p; }
     for (size_t i = 0; i < blocks.size();) {
-      if (!blocks[i].used && blocks.size() > 6) { cudaFree(blocks[i].p); blocks.erase(blocks.begin() + i); } else ++i;
+      if (!blocks[i].used && blocks.size() > 8) { cudaFree(blocks[i].p); if (blocks[i].ready) cudaEventDestroy(blocks[i].ready); blocks.erase(blocks.begin() + i); } else ++i;
     }
     void* p = nullptr;
     size_t cap = bytes + bytes / 8 + 4096;
     if (cudaMalloc(&p, cap) != cudaSuccess) { cap = bytes; if (cudaMalloc(&p, cap) != cudaSuccess) return nullptr; }
-    blocks.push_back({p, cap, true});
+    blocks.push_back({p, cap, true, nullptr, 0});
+    if (ready_out) *ready_out = nullptr;
     return p;
   }
-  void give_back(void* p) { for (auto& b : blocks) if (b.p == p) b.used = false; }
-  void release_all() { for (auto& b : blocks) cudaFree(b.p); blocks.clear(); }
+  // `st`: the stream whose queued work may still touch the block
+  void give_back(void* p, cudaStream_t st = nullptr) {
+    for (auto& b : blocks)
+      if (b.p == p) {
+        b.used = false;
+        b.stamp = ++clock;
+        if (!b.ready) cudaEventCreateWithFlags(&b.ready, cudaEventDisableTiming);
+        if (b.ready) cudaEventRecord(b.ready, st);
+      }
+  }
+  void release_all() { for (auto& b : blocks) { cudaFree(b.p); if (b.ready) cudaEventDestroy(b.ready); } blocks.clear(); }
 };
 
 extern "C" {

@@ -66,7 +66,6 @@ struct TileArgs {
   uint32_t n;                   // rows in the batch = stride of the scratch arrays; with n_dev: the CAPACITY the host sized everything for
   const uint32_t* n_dev;        // non-null: the number of rows is read here (FrameResult::n_records of this batch, still on the device when the
                                 // kernel is enqueued); more rows than `n` raise TF_OVERFLOW and nothing is decoded
-  int32_t* const* offs0;        // [n_var * 3] Arrow offsets arrays; uniform columns get offs[i] = i * L from this kernel
   uint32_t tile_cap;            // bytes of shared memory reserved for the record bytes of one tile (TILE_ROWS slots)
   uint32_t slot;                // bytes per record slot: an ODD multiple of 16 (bank-group spread, see crc_chunks)
   uint32_t verify;
@@ -203,7 +202,7 @@ __device__ __forceinline__ uint32_t crc_chunks(const uint32_t* g, const Tile& t,
 //   [0,16) mbarrier | CRC tables g5 2 KiB + xp16 2 KiB | seen words [32][4] u32 + CRC accumulators [32] | DevField[nf] | FieldTemplate[nf] | names | tile bytes
 // Everything between the mbarrier and the tile is constant per schema ("consts": built once per decoder in this layout,
 // api.cu) and arrives with ONE bulk copy on the same mbarrier as the tile.
-#define TILE_SEEN_BYTES (512u + 128u)      // seen words [32][4], then the CRC accumulators [32]; zero in the consts blob
+#define TILE_SEEN_BYTES (512u + 128u + 16u) // seen words [32][4], the CRC accumulators [32], then the mask of rows some warp gave up on; zero in the consts blob
 #define TILE_CRC_BYTES (2048u + 2048u)     // g5, xp16
 __host__ __device__ inline uint32_t tile_schema_smem(uint32_t nf, uint32_t names_bytes) {
   return ((nf * (uint32_t)sizeof(DevField) + 15u) & ~15u) + ((nf * (uint32_t)sizeof(FieldTemplate) + 15u) & ~15u) + ((names_bytes + 15u) & ~15u);
@@ -703,9 +702,12 @@ __global__ void __launch_bounds__(TILE_THREADS, TILE_MIN_CTAS) decode_tile_kerne
 #pragma unroll
     for (int k = 0; k < 4; ++k)
       if (w4[k] && (atomicOr(&sseen[lane * 4 + k], w4[k]) & w4[k])) bad = true;
+    if (bad) atomicOr(&sseen[160], 1u << lane);            // this row goes to the general path whatever else happens to it
   }
   asm volatile("bar.sync 1, %0;" ::"r"(TILE_PARSE_WARPS * 32) : "memory");
   {
+    // a row that some warp gave up on has fields that were never looked at: their absence says nothing about the shapes
+    const bool row_bad = (sseen[160] >> lane) & 1u;
     // ---- validity bitmaps by ballot (rows are 32-aligned), absent fields -> null / error; field f is finished by warp f % W ----
     uint32_t all[4];
 #pragma unroll
@@ -715,15 +717,6 @@ __global__ void __launch_bounds__(TILE_THREADS, TILE_MIN_CTAS) decode_tile_kerne
       const uint32_t wsel = f < 32 ? all[0] : f < 64 ? all[1] : f < 96 ? all[2] : all[3];
       const bool present = (wsel >> (f & 31)) & 1;
       const uint32_t m = __ballot_sync(FULLMASK, present && active);
-      if (A.offs0 && active && sfields[f].var_slot >= 0) {
-        // Arrow offsets of a uniform column are row * L: written here (coalesced, 32 rows per store), not by a separate launch
-        const int32_t vs = sfields[f].var_slot, ul = A.uniform_len[vs];
-        if (ul >= 0) {
-          int32_t* o = A.offs0[vs * 3];
-          o[row] = (int32_t)(row * (uint32_t)ul);
-          if (row + 1 == n_rows) o[n_rows] = (int32_t)(n_rows * (uint32_t)ul);
-        }
-      }
       if (active && !present && sfields[f].elem_type != TFR_T_NULL) {
         const DevField& fd = sfields[f];
         if (!fd.nullable) bad = true;                                         // NullPointerException: error path
@@ -732,7 +725,7 @@ __global__ void __launch_bounds__(TILE_THREADS, TILE_MIN_CTAS) decode_tile_kerne
           if (fd.width == 8) reinterpret_cast<uint64_t*>(vp)[row] = 0; else reinterpret_cast<uint32_t*>(vp)[row] = 0;
         } else if (fd.var_slot >= 0) {
           const int32_t ul = A.uniform_len[fd.var_slot];
-          if (ul > 0) shape_bad = 1;                                          // a null row has no values: not uniform
+          if (ul > 0 && !row_bad) shape_bad = 1;                              // a null row has no values: not uniform
           else if (ul < 0) for (int l = 0; l < fd.n_levels; ++l) A.cnt[(size_t)(fd.cnt_slot + l) * A.n + row] = 0;
         }
       }
@@ -747,11 +740,14 @@ __global__ void __launch_bounds__(TILE_THREADS, TILE_MIN_CTAS) decode_tile_kerne
   if (shape_bad) atomicOr(A.flags, TF_SHAPE | TF_FALLBACK);
 }
 
-// offsets of a uniform column: offs[i] = i * L  (i = 0..n)
+// offsets of a uniform column: offs[i] = i * L  (i = 0..n); n is read from the device when n_dev is given (pipelined submit:
+// the kernel runs on the frame-index stream, under the previous batch's tile kernel) and nothing is written when it exceeds
+// the capacity the arrays were sized for
 __global__ void uniform_offsets_kernel(int32_t* const* __restrict__ offs, uint32_t stride, const int32_t* __restrict__ uniform_len, uint32_t n_var,
-                                       uint32_t n) {
+                                       uint32_t n, const uint32_t* __restrict__ n_dev) {
   const uint32_t v = blockIdx.y;
   if (v >= n_var) return;
+  if (n_dev) { const uint32_t m = *n_dev; if (m > n) return; n = m; }
   const int32_t L = uniform_len[v];
   if (L < 0) return;
   int32_t* o = offs[v * stride];

@@ -167,16 +167,34 @@ def test_speculation_failures_are_redone_exactly(native, oracle):
         for _ in range(2):
             b, _ = dec.decode(good); b.release()
         assert dec.stats()["speculative_submits"] == 1
-        redone = 0
+
+        def steady():
+            """the decoder is (back) in the pipelined mode: a clean batch is submitted speculatively and not redone"""
+            s0 = dec.stats()
+            b = dec.submit(good); _check_batch(oracle, b, good, sch, what="steady state"); b.release()
+            s1 = dec.stats()
+            assert s1["speculative_submits"] == s0["speculative_submits"] + 1 and s1["speculative_redone"] == s0["speculative_redone"], (s0, s1)
+
+        def redone_exactly(data, what, code=None):
+            s0 = dec.stats()
+            b = dec.submit(data); _check_batch(oracle, b, data, sch, what=what)
+            if code is not None:
+                assert b.info["error_code"] == code
+            b.release()
+            s1 = dec.stats()
+            assert s1["speculative_submits"] == s0["speculative_submits"] + 1 and s1["speculative_redone"] == s0["speculative_redone"] + 1, (what, s0, s1)
+
         # payload bit flip in record 7000 -> Data crc32 checking failed at row 7000, rows before delivered
-        bad = _flip(good, int(offs[7000]) + 40)
-        b = dec.submit(bad); _check_batch(oracle, b, bad, sch, what="payload flip"); assert b.info["error_code"] == A.TFR_E_CRC_DATA; b.release(); redone += 1
+        redone_exactly(_flip(good, int(offs[7000]) + 40), "payload flip", A.TFR_E_CRC_DATA)
+        steady()
+        # a flip inside a list-length byte looks like a shape change to the kernel: still a CRC error, shapes kept
+        for pos in range(14, 40):
+            redone_exactly(_flip(good, int(offs[5000]) + pos), f"payload flip at +{pos}", A.TFR_E_CRC_DATA)
+        steady()
         # length flip in record 300 (low byte of the length): length CRC error at that row
-        bad = _flip(good, int(offs[300]))
-        b = dec.submit(bad); _check_batch(oracle, b, bad, sch, what="length flip"); assert b.info["error_code"] == A.TFR_E_CRC_LENGTH; b.release(); redone += 1
-        # steady state again afterwards
-        b = dec.submit(good); _check_batch(oracle, b, good, sch, what="good again"); b.release()
-        assert dec.stats()["speculative_redone"] == redone
+        redone_exactly(_flip(good, int(offs[300])), "length flip", A.TFR_E_CRC_LENGTH)
+        steady()
+        redone = dec.stats()["speculative_redone"]
         # shape change: FloatList[7] in one column of a second corpus -> count mode, then the new shapes are learned
         sch2, cols2 = cfg2_columns(9000, seed=6, float_len=7)
         other = _encode(oracle, sch2, cols2)
@@ -185,14 +203,15 @@ def test_speculation_failures_are_redone_exactly(native, oracle):
         st = dec.stats()
         assert st["shapes_learned"] == 2 and st["speculative_redone"] == redone + 1, st
         redone += 1
+        good = other
         # a non-canonical record (unpacked floats) among canonical ones: general path for the batch, identical rows
         k = 4000
         rec = bytes(other[record_offsets(other)[k] + 12: record_offsets(other)[k + 1] - 4])
         odd = pyref.frame_fast(rec + b"\x0a\x00")           # `features` field repeated (empty): merges, not canonical
         o2 = record_offsets(other)
         mixed = np.concatenate([other[: o2[k]], np.frombuffer(odd, np.uint8), other[o2[k + 1]:]])
-        b = dec.submit(mixed); _check_batch(oracle, b, mixed, sch, what="non-canonical record"); b.release(); redone += 1
-        assert dec.stats()["speculative_redone"] == redone
+        redone_exactly(mixed, "non-canonical record")
+        steady()
         # one record much larger than every slot seen so far (a long extra feature the schema ignores)
         def ld(tag, payload):
             return bytes([tag]) + pyref.varint(len(payload)) + payload
@@ -201,11 +220,7 @@ def test_speculation_failures_are_redone_exactly(native, oracle):
         assert rec[0] == 0x0A and rec[1] & 0x80
         rec2 = ld(0x0A, rec[3:] + entry)
         wide = np.concatenate([other[: o2[10]], np.frombuffer(pyref.frame_fast(rec2), np.uint8), other[o2[11]:]])
-        for _ in range(2):
-            b = dec.submit(other); b.release()
-        before = dec.stats()["speculative_redone"]
-        b = dec.submit(wide); _check_batch(oracle, b, wide, sch, what="record larger than the slot"); b.release()
-        assert dec.stats()["speculative_redone"] == before + 1
+        redone_exactly(wide, "record larger than the slot")
         b = dec.submit(wide); _check_batch(oracle, b, wide, sch, what="record larger than the slot, again"); b.release()
     finally:
         dec.close()

@@ -9,8 +9,7 @@ from spark_tfrecord_b200 import _native
 
 mib = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
 steps = int(sys.argv[2]) if len(sys.argv) > 2 else 200
-schema, n, batches = bench.make_batches(mib, 2, seed=2024, device=0)
-dev = [torch.from_numpy(b.copy()).cuda() for b in batches]
+schema, n, dev, batches = bench.make_device_pool(mib, 2, seed=2024, device=0, keep_host=2)
 dec = _native.Decoder(schema)
 for i in range(4):
     b, used = dec.decode(dev[i % 2]); assert b.info["error_code"] == 0; b.release()
