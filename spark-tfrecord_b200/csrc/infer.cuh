@@ -20,7 +20,8 @@ struct InferSlot {
   uint32_t flags;            // bit0: ArrayType(ArrayType(null)) seen (a FeatureList whose steps are all empty)
 };
 #define INFER_TABLE_SLOTS 65536u
-#define INFER_MAX_ENT 256      // entries of one map buffered per record for last-wins de-duplication
+#define INFER_MAX_ENT 1024     // entries of one map buffered per record for last-wins de-duplication; more raise INF_OVF_ENTRIES
+enum { INF_OVF_TABLE = 1u, INF_OVF_ENTRIES = 2u, INF_OVF_KEY = 4u };   // limits hit: reported as an explicit error, never as a silently wrong schema
 
 struct InferArgs {
   const uint8_t* data;
@@ -30,7 +31,7 @@ struct InferArgs {
   uint32_t record_type;
   const CrcTables* tabs;
   InferSlot* table;
-  uint32_t* first_err;       // [0] min failing record index, [1] its status (written by the thread that wins the min)
+  uint32_t* first_err;       // [0] min failing record index, [1] INF_OVF_* flags
   uint32_t* status;          // [n]
 };
 
@@ -45,7 +46,7 @@ __device__ __forceinline__ int feat_code(const FeatAcc& a) {       // inferField
   int base = a.kind == K_INT64 ? 1 : a.kind == K_FLOAT ? 2 : 3;
   return a.n > 1 ? base + 3 : base;
 }
-__device__ __forceinline__ void infer_merge(InferSlot* table, unsigned long long h, uint32_t name_off, uint32_t name_len, int code) {
+__device__ __forceinline__ void infer_merge(InferSlot* table, unsigned long long h, uint32_t name_off, uint32_t name_len, int code, uint32_t* ovf) {
   uint32_t slot = (uint32_t)(h ^ (h >> 32)) & (INFER_TABLE_SLOTS - 1);
   for (uint32_t probe = 0; probe < INFER_TABLE_SLOTS; ++probe) {
     unsigned long long cur = atomicCAS(&table[slot].hash, 0ull, h);
@@ -57,6 +58,7 @@ __device__ __forceinline__ void infer_merge(InferSlot* table, unsigned long long
     }
     slot = (slot + 1) & (INFER_TABLE_SLOTS - 1);
   }
+  atomicOr(ovf, INF_OVF_TABLE);            // more distinct names than slots
 }
 
 // one map (Features or FeatureLists) of one record: entries -> (hash, code, key) in shared memory, last wins, merge
@@ -113,11 +115,12 @@ __device__ __forceinline__ bool infer_map(const InferArgs& A, Cur body, bool is_
       }
     }
     if (__any_sync(FULLMASK, !ok)) return false;
+    if (lane < pend && klen >= (1u << 24)) atomicOr(&A.first_err[1], INF_OVF_KEY);
     if (lane < pend && nent + lane < INFER_MAX_ENT) {
       eh[nent + lane] = h; ecode[nent + lane] = (uint32_t)(code < 0 ? 0 : code) | (klen << 8); ekey[nent + lane] = koff;
     } else if (lane < pend) {
-      // beyond the de-duplication window: merged immediately (documented limit, > 256 entries in one map)
-      infer_merge(A.table, h, koff, klen, code < 0 ? 0 : code);
+      // beyond the de-duplication window: last-wins cannot be decided any more
+      atomicOr(&A.first_err[1], INF_OVF_ENTRIES);
     }
     nent = min(nent + pend, (uint32_t)INFER_MAX_ENT);
     pend = 0;
@@ -179,7 +182,7 @@ __global__ void __launch_bounds__(128) infer_kernel(InferArgs A) {
       for (uint32_t i = lane; i < nent; i += 32) {
         bool last = true;
         for (uint32_t j = i + 1; j < nent; ++j) if (eh[j] == eh[i]) { last = false; break; }
-        if (last) infer_merge(A.table, eh[i], ekey[i], ecode[i] >> 8, (int)(ecode[i] & 0xff));
+        if (last) infer_merge(A.table, eh[i], ekey[i], ecode[i] >> 8, (int)(ecode[i] & 0xff), &A.first_err[1]);
       }
       __syncwarp();
     }

@@ -27,7 +27,7 @@ from typing import Dict, Iterator, List, Optional, Sequence
 import numpy as np
 
 from . import _native
-from ._cabi import TFR_F_DEFAULT, columns_from_rows
+from ._cabi import TFR_F_DEFAULT, TFR_E_BATCH_TOO_LARGE as A_TFR_E_BATCH_TOO_LARGE, columns_from_rows
 from .sqltypes import RECORD_TYPES, StructType, byte_array_schema
 
 M = "src/main/scala/com/linkedin/spark/datasources/tfrecord/"
@@ -227,6 +227,29 @@ class PartitionedFile:
         return self.filePath
 
 
+def _stream_blocks(f, remaining: int, block: int, stage, process):
+    """The block loop shared by readFile and inferSchema: reads `f` in blocks of about `block` bytes into stage(nbytes) (a
+    writable uint8 array), calls process(buffer, nbytes, is_final) -> consumed bytes and carries the unconsumed tail (a
+    partial record) into the next block.  Yields after every block so that the caller can drain rows in between."""
+    carry = b""
+    while True:
+        want = min(max(block - len(carry), block // 2), remaining)   # a carried record larger than the block still makes progress
+        chunk = f.read(want) if want > 0 else b""
+        remaining -= len(chunk)
+        final = remaining == 0 or len(chunk) < want
+        nbytes = len(carry) + len(chunk)
+        st = stage(max(nbytes, 1))
+        if carry:
+            st[: len(carry)] = np.frombuffer(carry, dtype=np.uint8)
+        if chunk:
+            st[len(carry): nbytes] = np.frombuffer(chunk, dtype=np.uint8)
+        used = process(st, nbytes, final)
+        yield
+        carry = st[used:nbytes].tobytes()
+        if final:
+            return
+
+
 class TFRecordFileReader:
     BLOCK_BYTES = 256 << 20
 
@@ -247,36 +270,45 @@ class TFRecordFileReader:
                     if not compressed:
                         f.seek(file.start)
                     remaining = (1 << 62) if compressed else file.length          # a compressed file is read to its end
-                    carry = b""
-                    while True:
-                        want = min(max(block - len(carry), block // 2), remaining)   # a carried record larger than the block still makes progress
-                        chunk = f.read(want) if want > 0 else b""
-                        remaining -= len(chunk)
-                        final = remaining == 0 or len(chunk) < want
-                        nbytes = len(carry) + len(chunk)
-                        st = dec.staging(max(nbytes, 1))
-                        if carry:
-                            st[: len(carry)] = np.frombuffer(carry, dtype=np.uint8)
-                        if chunk:
-                            st[len(carry): nbytes] = np.frombuffer(chunk, dtype=np.uint8)
+                    todo = []
+
+                    def process(st, nbytes, final):
                         batch, used = dec.decode(st, is_final=final, nbytes=nbytes)
+                        todo.append(batch)
+                        return used
+
+                    for _ in _stream_blocks(f, remaining, block, dec.staging, process):
+                        batch = todo.pop()
                         try:
                             for row in _rows_of(batch):
                                 yield row
                             batch.raise_if_error()
                         finally:
                             batch.release()
-                        carry = st[used:nbytes].tobytes()
-                        if final:
-                            return
             finally:
                 dec.close()
 
         return gen()
 
 
+def _row_bytes(row) -> int:
+    """rough size of a buffered row's values (what decides when the writer flushes)"""
+    n = 0
+    for v in row:
+        if v is None:
+            continue
+        if isinstance(v, (bytes, bytearray, str)):
+            n += len(v) + 8
+        elif isinstance(v, (list, tuple)):
+            n += 8 + sum((len(x) + 8) if isinstance(x, (bytes, bytearray, str)) else (8 * len(x) + 8 if isinstance(x, (list, tuple)) else 8) for x in v)
+        else:
+            n += 8
+    return n + 16
+
+
 class TFRecordOutputWriter:
     FLUSH_ROWS = 1 << 16
+    FLUSH_BYTES = 256 << 20        # large rows (images, long byte strings) flush by size: one tfr_encode call frames < 2 GiB
 
     def __init__(self, path: str, options: Dict[str, str], dataSchema: StructType, context=None, device: int = 0):
         self.path = path
@@ -284,18 +316,30 @@ class TFRecordOutputWriter:
         self.schema = byte_array_schema() if self.recordType == 2 else dataSchema
         self._enc = _native.Encoder(self.schema, self.recordType, device)
         self._rows: List[tuple] = []
+        self._bytes = 0
         self._out = _open_write(path, _codec_name((options or {}).get("codec", "")))   # CodecStreams.createOutputStream (:19)
 
     def write(self, row: Sequence) -> None:
-        self._rows.append(tuple(row))
-        if len(self._rows) >= self.FLUSH_ROWS:
+        row = tuple(row)
+        self._rows.append(row)
+        self._bytes += _row_bytes(row)
+        if len(self._rows) >= self.FLUSH_ROWS or self._bytes >= self.FLUSH_BYTES:
             self._flush()
+
+    def _encode_rows(self, rows: List[tuple]) -> None:
+        try:
+            self._out.write(self._enc.encode(columns_from_rows(self.schema, rows, self.recordType)))
+        except _native.TfrError as e:
+            if e.code != A_TFR_E_BATCH_TOO_LARGE or len(rows) < 2:
+                raise
+            half = len(rows) // 2                                # the size estimate was too low: frame the rows in two calls
+            self._encode_rows(rows[:half])
+            self._encode_rows(rows[half:])
 
     def _flush(self):
         if self._rows:
-            cols = columns_from_rows(self.schema, self._rows, self.recordType)
-            self._out.write(self._enc.encode(cols))
-            self._rows = []
+            rows, self._rows, self._bytes = self._rows, [], 0
+            self._encode_rows(rows)
 
     def close(self) -> None:
         try:
@@ -329,10 +373,20 @@ class DefaultSource:
             mine = shard_lpt([os.path.getsize(f) for f in todo], dist.get_world_size())[dist.get_rank()]
             todo = [todo[i] for i in mine]
         inf = _native.Infer(rt, device)
+        block = TFRecordFileReader.BLOCK_BYTES
+        buf = [np.empty(0, dtype=np.uint8)]
+
+        def stage(nbytes):
+            if len(buf[0]) < nbytes:
+                buf[0] = np.empty(nbytes + nbytes // 8, dtype=np.uint8)
+            return buf[0]
+
         try:
-            for f in todo:
+            for f in todo:                       # streamed in blocks like readFile: files of any size, no whole-file copy
                 with _open_read(f) as fh:
-                    inf.update(fh.read())
+                    remaining = (1 << 62) if _codec_of_path(f) is not None else os.path.getsize(f)
+                    for _ in _stream_blocks(fh, remaining, block, stage, lambda st, nb, final: inf.update_block(st, final, nb)):
+                        pass
             local = inf.result()
         finally:
             inf.close()

@@ -15,5 +15,6 @@ struct JNIEnv {
   jobject GetObjectArrayElement(jobjectArray, jsize); void SetObjectArrayElement(jobjectArray, jsize, jobject);
   const char* GetStringUTFChars(jstring, jboolean*); void ReleaseStringUTFChars(jstring, const char*);
   void* GetDirectBufferAddress(jobject); jobject NewDirectByteBuffer(void*, jlong);
+  jstring NewStringUTF(const char*); jintArray NewIntArray(jsize); void SetIntArrayRegion(jintArray, jsize, jsize, const jint*);
   jlongArray NewLongArray(jsize); jobjectArray NewObjectArray(jsize, jclass, jobject); void SetLongArrayRegion(jlongArray, jsize, jsize, const jlong*);
 };

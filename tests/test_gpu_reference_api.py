@@ -314,3 +314,24 @@ def test_io_codec_option_and_read_by_extension(io, oracle, tmp_path, codec, ext)
 def test_io_unknown_codec_is_rejected(io, tmp_path):
     with pytest.raises(io.native.IllegalArgumentException):
         io.DefaultSource().save(str(tmp_path / "x"), exampleSchema, exampleTestRows, {"codec": "org.apache.hadoop.io.compress.SnappyCodec"})
+
+
+def test_output_writer_flushes_by_bytes_and_splits(io, oracle, tmp_path, monkeypatch):
+    """rows of tens of KiB each: the writer flushes on buffered bytes (not only on the row count) and halves a batch the
+    encoder refuses; the file is what the reference writer would have produced row by row"""
+    sch = StructType([StructField("img", BinaryType()), StructField("id", LongType())])
+    rng = np.random.default_rng(1)
+    rows = [(rng.integers(0, 256, 40_000, dtype=np.uint8).tobytes(), i) for i in range(300)]
+    monkeypatch.setattr(io.TFRecordOutputWriter, "FLUSH_BYTES", 1 << 20)
+    flushes = []
+    orig = io.TFRecordOutputWriter._encode_rows
+    monkeypatch.setattr(io.TFRecordOutputWriter, "_encode_rows", lambda self, r: (flushes.append(len(r)), orig(self, r))[1])
+    w = io.TFRecordOutputWriter(str(tmp_path / "big.tfrecord"), {}, sch)
+    for r in rows:
+        w.write(r)
+    w.close()
+    assert len(flushes) > 5 and max(flushes) < 100
+    data = (tmp_path / "big.tfrecord").read_bytes()
+    from spark_tfrecord_b200._cabi import columns_from_rows
+    want, rc, _ = oracle.encode(columns_from_rows(sch, rows), sch)
+    assert rc == 0 and data == want

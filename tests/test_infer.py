@@ -125,6 +125,52 @@ def test_gpu_infer_errors(oracle):
 
 
 @pytest.mark.gpu
+def test_gpu_infer_wide_maps_and_limits(oracle):
+    """hundreds of features in one record are de-duplicated exactly (Map.put: the LAST occurrence of a key decides, even when
+    an earlier one had the 'larger' type); past the device tables' limits the call fails loudly instead of guessing"""
+    from spark_tfrecord_b200 import _native
+    from oracle.pyref import ld, map_entry
+    ents = [map_entry(f"k{i:04d}".encode(), int64_feature(i).SerializeToString()) for i in range(700)]
+    ents[3] = map_entry(b"dup", float_feature(1.0, 2.0).SerializeToString())          # array<float> early ...
+    ents.append(map_entry(b"dup", int64_feature(5).SerializeToString()))                # ... Long wins: it is the last put
+    data = pyref.frame(ld(1, b"".join(ents)))
+    rc, want = oracle.infer(data, 0)
+    assert rc == 0 and want[b"dup"] == 1 and len(want) == 700
+    inf = _native.Infer(0); inf.update(data)
+    assert inf.result() == want
+    inf.close()
+    too_wide = pyref.frame(ld(1, b"".join(map_entry(f"k{i:05d}".encode(), int64_feature(i).SerializeToString()) for i in range(1500))))
+    inf = _native.Infer(0)
+    with pytest.raises(_native.TfrError) as ei:
+        inf.update(too_wide)
+    assert ei.value.code == A.TFR_E_BATCH_TOO_LARGE and "1024 features" in str(ei.value)
+    inf.close()
+
+
+@pytest.mark.gpu
+def test_default_source_infer_schema_streams_blocks(tmp_path, oracle, monkeypatch):
+    """inferSchema reads the file in blocks with a carried tail (files of any size): tiny blocks, same schema"""
+    from spark_tfrecord_b200 import io
+    from oracle.corpus import mixed_columns
+    sch, cols = mixed_columns(3000, seed=3)
+    data, rc, _ = oracle.encode(cols, sch)
+    assert rc == 0
+    p = tmp_path / "part-0.tfrecord"
+    p.write_bytes(data)
+    whole = io.DefaultSource().inferSchema({"recordType": "Example"}, [str(p)])
+    monkeypatch.setattr(io.TFRecordFileReader, "BLOCK_BYTES", 50_000)
+    blocks = io.DefaultSource().inferSchema({"recordType": "Example"}, [str(p)])
+    assert _as_map(blocks) == _as_map(whole) and len(whole) >= 8
+    rc, codes = oracle.infer(data, 0)
+    assert rc == 0 and _as_map(codes_to_struct(codes)) == _as_map(whole)
+    bad = tmp_path / "trunc.tfrecord"
+    bad.write_bytes(data[:-7])
+    from spark_tfrecord_b200 import _native
+    with pytest.raises(_native.IOException):
+        io.DefaultSource().inferSchema({"recordType": "Example"}, [str(bad)])
+
+
+@pytest.mark.gpu
 def test_default_source_infer_schema(tmp_path):
     from spark_tfrecord_b200 import io
     data, want = example_suite_data()
