@@ -80,12 +80,25 @@ struct TileArgs {
   uint32_t* cnt;                // [n_cnt][n]   (count mode)
   uint32_t* src;                // [n_var][n]
   uint8_t* cflag;               // [n_var][n]
-  const int32_t* uniform_len;   // [n_var] >= 0: speculated per-row count (elements, or bytes for scalar string/binary); -1: count mode
+  const int32_t* uniform_len;   // [n_var] >= 0: speculated per-row count (elements, or bytes for scalar string/binary); -1: count mode;
+                                // -2 (TILE_RAGGED): ragged column finished in THIS kernel (tile-local prefix + look-back across tiles)
+  // ---- one-pass ragged mode (any uniform_len == TILE_RAGGED) ----
+  uint32_t ragged;              // 1: tiles take ordered ids from `ticket`, publish per-array totals and look back for their bases
+  uint32_t n_cnt;               // count arrays (offset levels) of the schema
+  uint32_t* ticket;             // [1] zeroed per batch
+  uint32_t* lb_flag;            // [tiles] 0 nothing, 1 aggregates published, 2 inclusive prefixes published; zeroed per batch
+  uint32_t* lb_agg;             // [tiles][n_cnt] per-tile totals
+  unsigned long long* lb_pre;   // [tiles][n_cnt] inclusive prefixes
+  const unsigned long long* cap;     // [n_cnt] what each array's target buffer was sized for (elements of the next level / leaf values)
+  unsigned long long* totals;   // [n_cnt] grand totals, written by the last tile
+  int32_t* const* offs;         // [n_var*3] Arrow offsets arrays per level
+  const int32_t* var_field;     // [n_var] schema field of each var slot
   void* const* var_values;      // [n_var] leaf buffers (uniform mode)
   uint32_t* flags;              // [0] bit0: fall back to the general path, bit1: a uniform-shape speculation failed
 };
 
 enum { TF_FALLBACK = 1u, TF_SHAPE = 2u, TF_OVERFLOW = 4u };
+#define TILE_RAGGED (-2)
 
 // ---- mbarrier + bulk async copy (PTX; sm_90+) ---------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -113,6 +126,24 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t phase) {
         : "r"(smem_u32(bar)), "r"(phase)
         : "memory");
   } while (!ok);
+}
+
+// ---- look-back flags: release/acquire at GPU scope ----
+__device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_u32(uint32_t* p, uint32_t v) { asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+__device__ __forceinline__ uint32_t ld_cg_u32(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.global.cg.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ unsigned long long ld_cg_u64(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.global.cg.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
 }
 
 // ---- shared-memory byte helpers (offsets into the tile, not pointers: 32-bit address arithmetic) --
@@ -166,6 +197,16 @@ __device__ __forceinline__ bool t_len(const Tile& t, uint32_t& p, uint32_t end, 
   return false;
 }
 
+// l bytes of the tile -> global memory at any alignment: bytes up to the first aligned word, whole words, tail bytes.  The
+// 32 lanes of a warp copy the cells of 32 consecutive rows, which are adjacent in the output: the partial lines merge in L2.
+__device__ __forceinline__ void t_copy_out(const Tile& t, uint32_t src, uint8_t* dst, uint32_t l) {
+  uint32_t i = 0;
+  const uint32_t mis = (uint32_t)(reinterpret_cast<uintptr_t>(dst) & 3u);
+  if (mis) for (const uint32_t h = min(l, 4u - mis); i < h; ++i) dst[i] = (uint8_t)t.u8(src + i);
+  for (; i + 4 <= l; i += 4) *reinterpret_cast<uint32_t*>(dst + i) = t_u32(t, src + i);
+  for (; i < l; ++i) dst[i] = (uint8_t)t.u8(src + i);
+}
+
 // ---- per-thread CRC-32C over shared memory: 8 bytes per step through 13 conflict-free 5-bit tables (CrcTables::g5) ----
 __device__ __forceinline__ uint32_t crc_fold8(const uint32_t* g, uint32_t c, uint32_t lo, uint32_t hi) {
   const uint32_t a = lo ^ c;
@@ -208,8 +249,10 @@ __host__ __device__ inline uint32_t tile_schema_smem(uint32_t nf, uint32_t names
   return ((nf * (uint32_t)sizeof(DevField) + 15u) & ~15u) + ((nf * (uint32_t)sizeof(FieldTemplate) + 15u) & ~15u) + ((names_bytes + 15u) & ~15u);
 }
 __host__ __device__ inline uint32_t tile_const_bytes(uint32_t nf, uint32_t names_bytes) { return TILE_CRC_BYTES + TILE_SEEN_BYTES + tile_schema_smem(nf, names_bytes); }
-__host__ __device__ inline uint32_t tile_smem_bytes(uint32_t nf, uint32_t names_bytes, uint32_t tile_cap) {
-  return 16 + tile_const_bytes(nf, names_bytes) + tile_cap + 64;   // +64: template compares may look a few bytes past the tile
+// ragged mode scratch behind the tile: cell source offsets [n_var][32] | per-array counts -> local offsets [n_cnt][32] | totals [n_cnt] | bases u64 [n_cnt] | tile id
+__host__ __device__ inline uint32_t tile_ragged_bytes(uint32_t n_var, uint32_t n_cnt) { return (n_var + n_cnt) * 128u + n_cnt * 4u + n_cnt * 8u + 16u + 16u; }
+__host__ __device__ inline uint32_t tile_smem_bytes(uint32_t nf, uint32_t names_bytes, uint32_t tile_cap, uint32_t ragged_bytes = 0) {
+  return 16 + tile_const_bytes(nf, names_bytes) + tile_cap + 64 + ragged_bytes;   // +64: template compares may look a few bytes past the tile
 }
 
 template <bool SEQ>
@@ -228,13 +271,28 @@ __global__ void __launch_bounds__(TILE_THREADS, TILE_MIN_CTAS) decode_tile_kerne
 
   // Record r of the tile is copied into its own slot: bytes [off_r & ~15, off_r + framed length) -> tile + r * slot.
   // (cp.async.bulk wants 16-byte aligned source, destination and size; the record starts (off_r & 15) bytes into its slot.)
-  const uint32_t row0 = blockIdx.x * TILE_ROWS;
+  // ragged scratch behind the tile bytes (see tile_ragged_bytes)
+  uint32_t* rg_src = reinterpret_cast<uint32_t*>(tile_b + A.tile_cap + 64);           // [n_var][32] tile offset of each cell's bytes
+  uint32_t* rg_cnt = rg_src + (uint32_t)A.sch.n_var * 32u;                            // [n_cnt][32] counts, then tile-local exclusive offsets
+  uint32_t* rg_tot = rg_cnt + A.n_cnt * 32u;                                          // [n_cnt] tile totals
+  unsigned long long* rg_base = reinterpret_cast<unsigned long long*>(rg_tot + ((A.n_cnt + 1u) & ~1u) + 2u);   // [n_cnt] exclusive bases of this tile
+  uint32_t* rg_tile = rg_tot + ((A.n_cnt + 1u) & ~1u);                                // [0] tile id, [1] skip-copy flag
+  // Tile id.  Ragged mode: tiles look back at their predecessors' totals, so ids are handed out in start order (a tile only
+  // ever waits for tiles that are already running); otherwise the block index.
+  uint32_t tile = blockIdx.x;
+  if (A.ragged) {
+    if (threadIdx.x == 0) { rg_tile[0] = atomicAdd(A.ticket, 1u); rg_tile[1] = 0u; }
+    for (uint32_t i = threadIdx.x; i < A.n_cnt * 32u; i += TILE_THREADS) rg_cnt[i] = 0u;      // absent cells count as empty
+    __syncthreads();
+    tile = rg_tile[0];
+  }
+  const uint32_t row0 = tile * TILE_ROWS;
   uint32_t n_rows = A.n;
   if (A.n_dev) {
     n_rows = *A.n_dev;
     if (n_rows > A.n) {                                                    // more records than the host provisioned for: the host redoes the batch
-      if (blockIdx.x == 0 && threadIdx.x == 0) atomicOr(A.flags, TF_OVERFLOW | TF_FALLBACK);
-      return;
+      if (tile == 0 && threadIdx.x == 0) atomicOr(A.flags, TF_OVERFLOW | TF_FALLBACK);
+      return;                                                              // (no tile runs: nobody waits for anybody)
     }
     if (row0 >= n_rows) return;                                            // the grid was sized from the capacity
   }
@@ -250,7 +308,14 @@ __global__ void __launch_bounds__(TILE_THREADS, TILE_MIN_CTAS) decode_tile_kerne
   const bool clip = active && (off - head) + cbytes > A.nbytes;
   const uint32_t bulk_bytes = clip ? (A.nbytes - (off - head)) & ~15u : cbytes;
   if (__any_sync(FULLMASK, cbytes + 32u > A.slot)) {                       // a record too large for its slot: general path
-    if (threadIdx.x == 0) atomicOr(A.flags, TF_FALLBACK);
+    if (threadIdx.x == 0) {
+      atomicOr(A.flags, TF_FALLBACK);
+      if (A.ragged) {                                                      // successors must not wait for this tile (the batch is redone anyway)
+        for (uint32_t a = 0; a < A.n_cnt; ++a) A.lb_pre[(size_t)tile * A.n_cnt + a] = 0ull;
+        __threadfence();
+        st_release_u32(&A.lb_flag[tile], 2u);
+      }
+    }
     return;
   }
   if (wid == 0) {
@@ -463,7 +528,10 @@ __global__ void __launch_bounds__(TILE_THREADS, TILE_MIN_CTAS) decode_tile_kerne
           if (fd->depth == 0) {
             if (n == 0) { bad = true; break; }                                  // .head of an empty list: error path
             const int32_t ul = A.uniform_len[fd->var_slot];
-            if (ul >= 0) {
+            if (ul == TILE_RAGGED) {
+              rg_src[fd->var_slot * 32 + lane] = first_data;
+              rg_cnt[fd->cnt_slot * 32 + lane] = first_len;
+            } else if (ul >= 0) {
               if ((uint32_t)ul != first_len) shape_bad = 1;
               else {
                 uint8_t* dst = reinterpret_cast<uint8_t*>(A.var_values[fd->var_slot]) + (size_t)row * (uint32_t)ul;
@@ -481,11 +549,17 @@ __global__ void __launch_bounds__(TILE_THREADS, TILE_MIN_CTAS) decode_tile_kerne
               A.cflag[(size_t)fd->var_slot * A.n + row] = CF_CANON;
             }
           } else {
-            // ArrayType(String/Binary): two offset levels -> always count mode (never speculated)
+            // ArrayType(String/Binary): two offset levels -> ragged or count mode (never uniform)
+            if (A.uniform_len[fd->var_slot] == TILE_RAGGED) {
+              rg_src[fd->var_slot * 32 + lane] = body;
+              rg_cnt[fd->cnt_slot * 32 + lane] = n;
+              rg_cnt[(fd->cnt_slot + 1) * 32 + lane] = total;
+            } else {
             A.cnt[(size_t)fd->cnt_slot * A.n + row] = n;
             A.cnt[(size_t)(fd->cnt_slot + 1) * A.n + row] = total;
             A.src[(size_t)fd->var_slot * A.n + row] = body + g0;
             A.cflag[(size_t)fd->var_slot * A.n + row] = CF_CANON;
+            }
           }
         }
       } else {
@@ -544,7 +618,10 @@ __global__ void __launch_bounds__(TILE_THREADS, TILE_MIN_CTAS) decode_tile_kerne
             }
           } else {
             const int32_t ul = A.uniform_len[fd->var_slot];
-            if (ul >= 0) {
+            if (ul == TILE_RAGGED) {
+              rg_src[fd->var_slot * 32 + lane] = pk;
+              rg_cnt[fd->cnt_slot * 32 + lane] = n;
+            } else if (ul >= 0) {
               if ((uint32_t)ul != n) shape_bad = 1;
               else if (kind == K_FLOAT) {
                 if (fd->elem_type == TFR_T_FLOAT32) {
@@ -705,6 +782,126 @@ __global__ void __launch_bounds__(TILE_THREADS, TILE_MIN_CTAS) decode_tile_kerne
     if (bad) atomicOr(&sseen[160], 1u << lane);            // this row goes to the general path whatever else happens to it
   }
   asm volatile("bar.sync 1, %0;" ::"r"(TILE_PARSE_WARPS * 32) : "memory");
+  if (A.ragged) {
+    // ================= ragged columns, finished in this pass =================
+    // (T) tile-local exclusive prefix of every count array over the 32 rows (lane = row); array a by warp a % W
+    for (uint32_t a = wid; a < A.n_cnt; a += TILE_PARSE_WARPS) {
+      const uint32_t c = rg_cnt[a * 32 + lane];
+      uint32_t tot;
+      const uint32_t ex = warp_excl_scan_u32(c, tot);
+      rg_cnt[a * 32 + lane] = ex;
+      if (lane == 0) rg_tot[a] = tot;
+    }
+    asm volatile("bar.sync 1, %0;" ::"r"(TILE_PARSE_WARPS * 32) : "memory");
+    // (L) bases across tiles: warp 0 publishes this tile's totals, then looks back over its predecessors' totals until it
+    //     meets one whose inclusive prefix is known (decoupled look-back, one flag per tile, lane = array when summing)
+    if (wid == 0) {
+      const uint32_t nc = A.n_cnt;
+      for (uint32_t a = lane; a < nc; a += 32) A.lb_agg[(size_t)tile * nc + a] = rg_tot[a];
+      __threadfence();
+      __syncwarp();
+      if (lane == 0) st_release_u32(&A.lb_flag[tile], 1u);
+      unsigned long long run[4] = {0ull, 0ull, 0ull, 0ull};                     // arrays lane, lane+32, lane+64, lane+96 (n_cnt <= 128)
+      bool give_up = false;
+      int32_t p = (int32_t)tile - 1;
+      uint32_t spins = 0;
+      while (p >= 0) {
+        const int32_t q = p - (int32_t)lane;                                     // lane k looks at tile p - k
+        const uint32_t fl = q >= 0 ? ld_acquire_u32(&A.lb_flag[q]) : 2u;         // in front of tile 0: prefix 0
+        const uint32_t pre_mask = __ballot_sync(FULLMASK, fl == 2u);
+        const uint32_t first_pre = pre_mask ? (uint32_t)__ffs((int)pre_mask) - 1u : 32u;
+        const uint32_t need = first_pre >= 31u ? 0xffffffffu : (2u << first_pre) - 1u;   // lanes 0 .. first_pre
+        if (__ballot_sync(FULLMASK, fl == 0u) & need) {                          // a predecessor has not published yet
+          // the batch is being abandoned (another tile raised the fallback flag), or something is badly wrong: never hang
+          if ((++spins & 63u) == 0u && ((ld_cg_u32(A.flags) & TF_FALLBACK) || spins > (1u << 24))) { give_up = true; break; }
+          __nanosleep(40);
+          continue;
+        }
+        __threadfence();
+        const uint32_t kmax = min(first_pre, 31u);
+        for (uint32_t k = 0; k <= kmax; ++k) {
+          const int32_t t2 = p - (int32_t)k;
+          if (t2 < 0) break;
+          const bool is_pre = k == first_pre;
+#pragma unroll
+          for (uint32_t j = 0; j < 4; ++j) {
+            const uint32_t a = lane + 32u * j;
+            if (a < nc) run[j] += is_pre ? ld_cg_u64(&A.lb_pre[(size_t)t2 * nc + a]) : (unsigned long long)ld_cg_u32(&A.lb_agg[(size_t)t2 * nc + a]);
+          }
+        }
+        if (first_pre < 32u) break;
+        p -= 32;
+      }
+      bool over = false;
+#pragma unroll
+      for (uint32_t j = 0; j < 4; ++j) {
+        const uint32_t a = lane + 32u * j;
+        if (a < nc) {
+          const unsigned long long incl = run[j] + rg_tot[a];
+          rg_base[a] = run[j];
+          A.lb_pre[(size_t)tile * nc + a] = incl;
+          if (incl > A.cap[a] || incl > 0x7fffffffull) over = true;             // target buffer (or int32 offsets) too small: host redoes the batch
+          if (row0 + TILE_ROWS >= n_rows) A.totals[a] = incl;                    // the last tile knows the grand totals
+        }
+      }
+      __threadfence();
+      __syncwarp();
+      if (lane == 0) st_release_u32(&A.lb_flag[tile], 2u);
+      over = __any_sync(FULLMASK, over);
+      if (give_up || over) {
+        if (lane == 0) { rg_tile[1] = 1u; atomicOr(A.flags, over ? (TF_OVERFLOW | TF_FALLBACK) : TF_FALLBACK); }
+      }
+    }
+    asm volatile("bar.sync 1, %0;" ::"r"(TILE_PARSE_WARPS * 32) : "memory");
+    // (C) offsets + values: column v by warp v % W, lane = row.  Cells of consecutive rows are adjacent in the output.
+    if (!rg_tile[1]) {
+      for (uint32_t v = wid; v < (uint32_t)A.sch.n_var; v += TILE_PARSE_WARPS) {
+        if (A.uniform_len[v] != TILE_RAGGED) continue;
+        const DevField& fd = sfields[A.var_field[v]];
+        const uint32_t a0 = (uint32_t)fd.cnt_slot;
+        const uint32_t ex0 = rg_cnt[a0 * 32 + lane];
+        const uint32_t c0 = (lane == 31 ? rg_tot[a0] : rg_cnt[a0 * 32 + lane + 1]) - ex0;       // this row's count at level 0
+        const unsigned long long b0 = rg_base[a0];
+        const bool last_row = row + 1 == n_rows;
+        if (!active) continue;
+        int32_t* o0 = A.offs[v * 3];
+        o0[row] = (int32_t)(b0 + ex0);
+        if (last_row) o0[n_rows] = (int32_t)(b0 + ex0 + c0);
+        if (c0 == 0) { if (last_row && fd.n_levels == 2) A.offs[v * 3 + 1][b0 + ex0] = (int32_t)(rg_base[a0 + 1] + rg_cnt[(a0 + 1) * 32 + lane]); continue; }
+        const uint32_t src = rg_src[v * 32 + lane];
+        uint8_t* vals = reinterpret_cast<uint8_t*>(A.var_values[v]);
+        if (fd.depth == 0) {                                   // scalar string / binary: c0 bytes
+          t_copy_out(T, src, vals + b0 + ex0, c0);
+        } else if (fd.kind == K_FLOAT) {                       // packed floats
+          if (fd.elem_type == TFR_T_FLOAT32) { uint32_t* d = reinterpret_cast<uint32_t*>(vals) + b0 + ex0; for (uint32_t i = 0; i < c0; ++i) d[i] = t_u32(T, src + 4 * i); }
+          else { double* d = reinterpret_cast<double*>(vals) + b0 + ex0; for (uint32_t i = 0; i < c0; ++i) d[i] = (double)__uint_as_float(t_u32(T, src + 4 * i)); }
+        } else if (fd.kind == K_INT64) {                       // packed varints (validated by the parse)
+          uint32_t q = src;
+          for (uint32_t i = 0; i < c0; ++i) {
+            uint64_t x = 0; uint32_t sh = 0;
+            for (;;) { const uint32_t b = T.u8(q++); x |= (uint64_t)(b & 0x7f) << sh; sh += 7; if (b < 0x80) break; }
+            if (fd.elem_type == TFR_T_INT64) reinterpret_cast<int64_t*>(vals)[b0 + ex0 + i] = (int64_t)x;
+            else reinterpret_cast<int32_t*>(vals)[b0 + ex0 + i] = (int32_t)(uint32_t)x;
+          }
+        } else {                                               // list of strings / binaries: { 0A blen bytes }*, inner offsets + bytes
+          int32_t* o1 = A.offs[v * 3 + 1];
+          unsigned long long vpos = rg_base[a0 + 1] + rg_cnt[(a0 + 1) * 32 + lane];
+          uint32_t q = src;
+          for (uint32_t i = 0; i < c0; ++i) {
+            uint32_t bl = 0;
+            ++q;                                               // 0A
+            uint32_t qq = q;
+            t_len(T, qq, q + 5, bl);
+            q = qq;
+            o1[b0 + ex0 + i] = (int32_t)vpos;
+            t_copy_out(T, q, vals + vpos, bl);
+            vpos += bl; q += bl;
+          }
+          if (last_row) o1[b0 + ex0 + c0] = (int32_t)vpos;
+        }
+      }
+    }
+  }
   {
     // a row that some warp gave up on has fields that were never looked at: their absence says nothing about the shapes
     const bool row_bad = (sseen[160] >> lane) & 1u;
@@ -726,11 +923,11 @@ __global__ void __launch_bounds__(TILE_THREADS, TILE_MIN_CTAS) decode_tile_kerne
         } else if (fd.var_slot >= 0) {
           const int32_t ul = A.uniform_len[fd.var_slot];
           if (ul > 0 && !row_bad) shape_bad = 1;                              // a null row has no values: not uniform
-          else if (ul < 0) for (int l = 0; l < fd.n_levels; ++l) A.cnt[(size_t)(fd.cnt_slot + l) * A.n + row] = 0;
+          else if (ul == -1) for (int l = 0; l < fd.n_levels; ++l) A.cnt[(size_t)(fd.cnt_slot + l) * A.n + row] = 0;
         }
       }
       if (lane == 0) {
-        reinterpret_cast<uint32_t*>(A.bitmaps + (size_t)f * A.nb_stride)[blockIdx.x] = m;
+        reinterpret_cast<uint32_t*>(A.bitmaps + (size_t)f * A.nb_stride)[tile] = m;
         const uint32_t nulls = __popc(act_mask & ~m);
         if (nulls) atomicAdd(&A.null_counts[f], (unsigned long long)nulls);
       }

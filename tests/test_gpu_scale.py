@@ -360,3 +360,66 @@ def test_device_buffer_ending_exactly_at_nbytes(native, oracle):
         dec.close()
         for p in ptrs:
             rt.cudaFree(p)
+
+
+def test_ragged_columns_one_pass_matches_oracle(native, oracle):
+    """ragged columns in the pipelined mode: the tile kernel finishes them itself (tile-local prefix + look-back across
+    tiles) -- scalar strings / binaries, lists of every element type, lists of strings, nulls, empty lists, many tiles"""
+    from oracle.corpus import mixed_columns
+    sch, _ = mixed_columns(10, seed=1)
+    datas = [_encode(oracle, sch, mixed_columns(n, seed=40 + i)[1]) for i, n in enumerate([30000, 30000, 30011, 25000, 33000, 31, 30000])]
+    dec = native.Decoder(sch)
+    try:
+        b, _ = dec.decode(datas[0]); _check_batch(oracle, b, datas[0], sch, what="learning batch"); b.release()
+        inflight = [(i, dec.submit(datas[i])) for i in range(1, 4)]
+        for i, b in inflight:
+            _check_batch(oracle, b, datas[i], sch, what=f"ragged batch {i}"); b.release()
+        for i in range(4, len(datas)):
+            b = dec.submit(datas[i]); _check_batch(oracle, b, datas[i], sch, what=f"ragged batch {i}"); b.release()
+        st = dec.stats()
+        assert st["speculative_submits"] >= 5 and st["speculative_redone"] <= 1, st      # (the 31-record batch may be too small to speculate on)
+        assert st["count_mode_batches"] <= 2, st
+    finally:
+        dec.close()
+
+
+def test_ragged_bytes_cfg2_steady_state(native, oracle):
+    """configs[1] with BytesList values of 0..40 bytes: float lists stay uniform, bytes columns are ragged; 300 k records"""
+    import importlib.util, os, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("bench_mod2", os.path.join(root, "bench.py"))
+    bm = importlib.util.module_from_spec(spec)
+    argv, sys.argv = sys.argv, ["bench.py"]
+    try:
+        spec.loader.exec_module(bm)
+    finally:
+        sys.argv = argv
+    sch, cols = bm.cfg2_schema_and_columns(300_000, seed=777, ragged_bytes=True)
+    data = _encode(oracle, sch, cols)
+    dec = native.Decoder(sch)
+    try:
+        for it in range(3):
+            b = dec.submit(data)
+            assert b.info["error_code"] == 0 and b.n_rows == 300_000
+            got = b.to_host()
+            assert_columns_equal(got, cols, sch.names, f"ragged cfg2 decode #{it + 1} vs source")
+            if it == 2:
+                oracle_check_slices(oracle, data, sch, got, n_slices=8, what="ragged cfg2 vs oracle")
+            b.release()
+        st = dec.stats()
+        assert st["speculative_submits"] == 2 and st["speculative_redone"] == 0 and st["count_mode_batches"] == 1, st
+        # a batch whose strings are much longer than the capacities learned: flagged (capacity), redone, relearned
+        sch2, cols2 = bm.cfg2_schema_and_columns(20_000, seed=778, ragged_bytes=True)
+        from spark_tfrecord_b200._cabi import HostColumn
+        rng = np.random.default_rng(5)
+        for i in range(48, 64):
+            lens = rng.integers(100, 200, 20_000)
+            offs = np.concatenate([[0], np.cumsum(lens)]).astype(np.int32)
+            cols2[i] = HostColumn(A.TFR_T_BINARY, 0, 20_000, cols2[i].validity, [offs], rng.integers(0, 256, int(offs[-1]), dtype=np.uint8))
+        longer = _encode(oracle, sch2, cols2)
+        b = dec.submit(longer); _check_batch(oracle, b, longer, sch, what="longer strings than provisioned"); b.release()
+        assert dec.stats()["speculative_redone"] == 1
+        b = dec.submit(longer); _check_batch(oracle, b, longer, sch, what="longer strings, capacities relearned"); b.release()
+        assert dec.stats()["speculative_redone"] == 1
+    finally:
+        dec.close()
