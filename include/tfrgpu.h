@@ -123,10 +123,10 @@ int32_t tfr_decoder_num_staging_slots(void);
  *   data/nbytes : framed TFRecord bytes (u64 len | u32 maskedcrc(len) | payload | u32 maskedcrc)
  *                 starting at a record boundary; in host memory (pageable or the pinned
  *                 staging above) or in device memory (data_on_device != 0).  Device input: any
- *                 alignment is accepted (a 16-byte aligned pointer gets the single-pass tile
- *                 kernels) and NO padding behind data + nbytes is required: the kernels never
- *                 touch a 4-byte aligned word that holds no byte of the buffer.  The buffer must
- *                 stay valid and unchanged until the batch has been waited on.
+ *                 alignment gets the single-pass tile kernels, and NO padding around the buffer is
+ *                 required: 16-byte groups that cross data or data + nbytes are never bulk-copied,
+ *                 and no 4-byte aligned word that holds no byte of the buffer is ever touched.
+ *                 The buffer must stay valid and unchanged until the batch has been waited on.
  *   is_final    : nonzero -> a trailing partial record is TFR_E_TRUNCATED (EOF inside a
  *                 record); zero -> it is left unconsumed (see *consumed).
  * tfr_decode returns when the batch is complete and verified (*consumed is final).

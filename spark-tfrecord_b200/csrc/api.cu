@@ -3,6 +3,7 @@
 // ownership, host copies and Arrow C Data Interface export.  No torch types, no CPU fallback: every
 // compute path below launches the sm_100a kernels of frame.cuh / decode.cuh / scan.cuh / encode.cuh.
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>      // header-only NVTX 3: ranges show up in Nsight Systems / ncu --nvtx, cost nothing when no tool is attached
 #include <algorithm>
 #include <atomic>
 #include <cstdio>
@@ -40,6 +41,12 @@ int32_t DevBuf::ensure(size_t bytes) {
   return TFR_OK;
 }
 #define TRY(expr) do { int32_t _rc = (expr); if (_rc) return _rc; } while (0)
+
+// NVTX range over one C-ABI call (the tracing hook of this path)
+struct NvtxRange {
+  explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
+};
 
 extern "C" int32_t tfr_abi_version(void) { return TFR_ABI_VERSION; }
 extern "C" const char* tfr_last_error(void) { return g_last_error.c_str(); }

@@ -60,8 +60,9 @@ struct FieldTemplate {
 };
 
 struct TileArgs {
-  const uint8_t* data;
+  const uint8_t* data;          // framed bytes, any alignment
   uint32_t nbytes;
+  uint32_t misalign;            // data & 15
   const uint32_t* rec_off;      // [n+1]
   uint32_t n;                   // rows in the batch = stride of the scratch arrays; with n_dev: the CAPACITY the host sized everything for
   const uint32_t* n_dev;        // non-null: the number of rows is read here (FrameResult::n_records of this batch, still on the device when the
@@ -250,13 +251,17 @@ __host__ __device__ inline uint32_t tile_schema_smem(uint32_t nf, uint32_t names
 }
 __host__ __device__ inline uint32_t tile_const_bytes(uint32_t nf, uint32_t names_bytes) { return TILE_CRC_BYTES + TILE_SEEN_BYTES + tile_schema_smem(nf, names_bytes); }
 // ragged mode scratch behind the tile: cell source offsets [n_var][32] | per-array counts -> local offsets [n_cnt][32] | totals [n_cnt] | bases u64 [n_cnt] | tile id
-__host__ __device__ inline uint32_t tile_ragged_bytes(uint32_t n_var, uint32_t n_cnt) { return (n_var + n_cnt) * 128u + n_cnt * 4u + n_cnt * 8u + 16u + 16u; }
+__host__ __device__ inline uint32_t tile_ragged_bytes(uint32_t n_var, uint32_t n_cnt) { return (n_var + n_cnt) * 128u + n_cnt * 4u + n_cnt * 8u + 16u + 16u + 64u; }
 __host__ __device__ inline uint32_t tile_smem_bytes(uint32_t nf, uint32_t names_bytes, uint32_t tile_cap, uint32_t ragged_bytes = 0) {
   return 16 + tile_const_bytes(nf, names_bytes) + tile_cap + 64 + ragged_bytes;   // +64: template compares may look a few bytes past the tile
 }
 
-template <bool SEQ>
-__global__ void __launch_bounds__(TILE_THREADS, TILE_MIN_CTAS) decode_tile_kernel(TileArgs A) {
+// PW parse warps + CW CRC warps per tile.  Large records: shared memory allows three tiles per SM, so a tile gets 12 + 3 warps
+// (45 resident warps).  Small records: a tile is a few KB, eight fit an SM, and 4 + 1 warps per tile give the same number of
+// resident warps with three times as many records in flight (a tile's life is a latency chain: offsets -> bulk copy -> parse
+// -> barriers -> stores) and a third of the hops (every parse warp walks every entry).
+template <bool SEQ, bool RG, int PW, int CW>
+__global__ void __launch_bounds__((PW + CW) * 32, (PW >= 12 ? TILE_MIN_CTAS : 8)) decode_tile_kernel(TileArgs A) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
   uint32_t* s8 = reinterpret_cast<uint32_t*>(smem_raw + 16);                               // g5 tables, then xp16
@@ -275,14 +280,14 @@ __global__ void __launch_bounds__(TILE_THREADS, TILE_MIN_CTAS) decode_tile_kerne
   uint32_t* rg_src = reinterpret_cast<uint32_t*>(tile_b + A.tile_cap + 64);           // [n_var][32] tile offset of each cell's bytes
   uint32_t* rg_cnt = rg_src + (uint32_t)A.sch.n_var * 32u;                            // [n_cnt][32] counts, then tile-local exclusive offsets
   uint32_t* rg_tot = rg_cnt + A.n_cnt * 32u;                                          // [n_cnt] tile totals
-  unsigned long long* rg_base = reinterpret_cast<unsigned long long*>(rg_tot + ((A.n_cnt + 1u) & ~1u) + 2u);   // [n_cnt] exclusive bases of this tile
-  uint32_t* rg_tile = rg_tot + ((A.n_cnt + 1u) & ~1u);                                // [0] tile id, [1] skip-copy flag
+  unsigned long long* rg_base = reinterpret_cast<unsigned long long*>(rg_tot + ((A.n_cnt + 1u) & ~1u) + 16u);  // [n_cnt] exclusive bases of this tile
+  uint32_t* rg_tile = rg_tot + ((A.n_cnt + 1u) & ~1u);                                // [0] tile id, [1] skip-copy flag, [2..14) look-back summaries of the warps
   // Tile id.  Ragged mode: tiles look back at their predecessors' totals, so ids are handed out in start order (a tile only
   // ever waits for tiles that are already running); otherwise the block index.
   uint32_t tile = blockIdx.x;
-  if (A.ragged) {
-    if (threadIdx.x == 0) { rg_tile[0] = atomicAdd(A.ticket, 1u); rg_tile[1] = 0u; }
-    for (uint32_t i = threadIdx.x; i < A.n_cnt * 32u; i += TILE_THREADS) rg_cnt[i] = 0u;      // absent cells count as empty
+  if (RG) {
+    if (threadIdx.x == 0) { rg_tile[0] = atomicAdd(A.ticket, 1u); rg_tile[1] = 0u; rg_tile[2 + PW] = 0u; }
+    for (uint32_t i = threadIdx.x; i < A.n_cnt * 32u; i += ((PW + CW) * 32)) rg_cnt[i] = 0u;      // absent cells count as empty
     __syncthreads();
     tile = rg_tile[0];
   }
@@ -301,17 +306,25 @@ __global__ void __launch_bounds__(TILE_THREADS, TILE_MIN_CTAS) decode_tile_kerne
   const uint32_t row = row0 + lane;
   uint32_t off = 0, flen = 16;
   if (active) { off = A.rec_off[row]; flen = A.rec_off[row + 1] - off; }
-  const uint32_t head = off & 15u;
+  // cp.async.bulk wants 16-byte aligned source, destination and size.  Coordinates below are bytes from the 16-byte aligned
+  // address at or below A.data (`base`): the buffer is [mis, lim).  A record's 16-byte groups that are not entirely inside the
+  // buffer -- the first group of a misaligned buffer, the last group of the batch's last record -- are clipped from the bulk
+  // copy and their bytes inside the buffer are moved with ordinary loads: a caller's device buffer needs neither alignment
+  // nor padding.
+  const uint32_t mis = A.misalign, lim = mis + A.nbytes;
+  const uint8_t* base = A.data - mis;
+  const uint32_t head = (off + mis) & 15u;
+  const uint32_t g_lo = off + mis - head;                                  // the record's first 16-byte group
   const uint32_t cbytes = active ? (head + flen + 15u) & ~15u : 0u;
-  // the last 16-byte group of the batch's last record may cross data + nbytes: a caller's device buffer need not be padded,
-  // so that group is clipped from the bulk copy and its bytes inside the buffer are moved with ordinary loads
-  const bool clip = active && (off - head) + cbytes > A.nbytes;
-  const uint32_t bulk_bytes = clip ? (A.nbytes - (off - head)) & ~15u : cbytes;
+  uint32_t b_lo = g_lo, b_hi = g_lo + cbytes;
+  if (active && b_lo < mis) b_lo += 16u;
+  if (active && b_hi > lim) b_hi = lim & ~15u;
+  const uint32_t bulk_bytes = (active && b_hi > b_lo) ? b_hi - b_lo : 0u;
   if (__any_sync(FULLMASK, cbytes + 32u > A.slot)) {                       // a record too large for its slot: general path
     if (threadIdx.x == 0) {
       atomicOr(A.flags, TF_FALLBACK);
-      if (A.ragged) {                                                      // successors must not wait for this tile (the batch is redone anyway)
-        for (uint32_t a = 0; a < A.n_cnt; ++a) A.lb_pre[(size_t)tile * A.n_cnt + a] = 0ull;
+      if (RG) {                                                            // successors must not wait for this tile (the batch is redone anyway)
+        for (uint32_t a = 0; a < A.n_cnt; ++a) A.lb_pre[(size_t)tile * ((A.n_cnt + 3u) & ~3u) + a] = 0ull;
         __threadfence();
         st_release_u32(&A.lb_flag[tile], 2u);
       }
@@ -329,8 +342,13 @@ __global__ void __launch_bounds__(TILE_THREADS, TILE_MIN_CTAS) decode_tile_kerne
       bulk_g2s(smem_raw + 16, A.consts, A.const_bytes, bar);      // CRC tables, zeroed seen words, schema, templates, names
     }
     __syncwarp();
-    if (bulk_bytes) bulk_g2s(tile_b + lane * A.slot, A.data + (off - head), bulk_bytes, bar);
-    if (clip) for (uint32_t i = (off - head) + bulk_bytes; i < A.nbytes; ++i) tile_b[lane * A.slot + (i - (off - head))] = A.data[i];
+    if (bulk_bytes) bulk_g2s(tile_b + lane * A.slot + (b_lo - g_lo), base + b_lo, bulk_bytes, bar);
+    if (active) {
+      uint8_t* sl = tile_b + lane * A.slot;
+      const uint32_t e1 = min(b_lo, lim);
+      if (b_lo > g_lo) for (uint32_t i = mis; i < e1; ++i) sl[i - g_lo] = base[i];                                  // clipped first group
+      if (b_hi < g_lo + cbytes) for (uint32_t i = max(b_hi, e1); i < lim; ++i) sl[i - g_lo] = base[i];             // clipped last group
+    }
   }
   __syncthreads();                                                // the barrier is initialised before anyone waits on it
   mbar_wait(bar, 0);
@@ -344,8 +362,8 @@ __global__ void __launch_bounds__(TILE_THREADS, TILE_MIN_CTAS) decode_tile_kerne
   asm volatile("mov.u32 %0, %1;" : "=r"(T.s) : "r"(smem_u32(tile_b)) : "memory");   // ordered after mbar_wait
 
   // =============================== warps W .. W+C-1: CRC ===============================
-  if (wid >= TILE_PARSE_WARPS) {
-    const uint32_t cw = wid - TILE_PARSE_WARPS;
+  if (wid >= PW) {
+    const uint32_t cw = wid - PW;
     uint32_t* scrc = sseen + 128;
     const uint32_t* xp16 = s8 + 512;
     const bool on = active && A.verify;
@@ -358,15 +376,15 @@ __global__ void __launch_bounds__(TILE_THREADS, TILE_MIN_CTAS) decode_tile_kerne
         c = 0xFFFFFFFFu;
         for (uint32_t i = 0; i < hn; ++i) c = crc_byte(s8, c, T.u8(pay + i));
       }
-      if (cw == TILE_CRC_WARPS - 1) {
+      if (cw == CW - 1) {
         // the frame index chained the headers without checking them on the fast path: check the length CRC here
         if (crc_mask(~crc_fold8(s8, 0xFFFFFFFFu, t_u32(T, pay - 12), t_u32(T, pay - 8))) != t_u32(T, pay - 4)) atomicOr(A.flags, TF_FALLBACK);
       }
-      const uint32_t k0 = K * cw / TILE_CRC_WARPS, k1 = K * (cw + 1) / TILE_CRC_WARPS;
+      const uint32_t k0 = K * cw / CW, k1 = K * (cw + 1) / CW;
       c = crc_chunks(s8, T, b0 + 16 * k0, k1 - k0, c);
       if (c) atomicXor(&scrc[lane], K - k1 ? gf2_mulmod(xp16[K - k1], c) : c);
     }
-    asm volatile("bar.sync 2, %0;" ::"r"(TILE_CRC_WARPS * 32) : "memory");
+    asm volatile("bar.sync 2, %0;" ::"r"(CW * 32) : "memory");
     if (cw == 0 && on) {
       uint32_t c = scrc[lane];
       for (uint32_t o = b0 + 16 * K; o < end; ++o) c = crc_byte(s8, c, T.u8(o));
@@ -417,7 +435,7 @@ __global__ void __launch_bounds__(TILE_THREADS, TILE_MIN_CTAS) decode_tile_kerne
         }
       }
       if (bad || p >= cend) break;
-      skip = TILE_PARSE_WARPS - 1;                           // this entry is ours; W - 1 hops to the next
+      skip = PW - 1;                           // this entry is ours; W - 1 hops to the next
       // ---- owned entry: try the expected field's template first ----
       uint32_t eend, kind, llen;
       int f = -1;
@@ -498,7 +516,7 @@ __global__ void __launch_bounds__(TILE_THREADS, TILE_MIN_CTAS) decode_tile_kerne
           if (seen_hi & b64) { bad = true; break; }
           seen_hi |= b64;
         }
-        next_f = (uint32_t)f + TILE_PARSE_WARPS;
+        next_f = (uint32_t)f + PW;
         if (fd->depth > 1) { bad = true; break; }                                 // nesting in a Feature: error path
       }
       if (kind == K_BYTES) {
@@ -528,7 +546,7 @@ __global__ void __launch_bounds__(TILE_THREADS, TILE_MIN_CTAS) decode_tile_kerne
           if (fd->depth == 0) {
             if (n == 0) { bad = true; break; }                                  // .head of an empty list: error path
             const int32_t ul = A.uniform_len[fd->var_slot];
-            if (ul == TILE_RAGGED) {
+            if (RG && ul == TILE_RAGGED) {
               rg_src[fd->var_slot * 32 + lane] = first_data;
               rg_cnt[fd->cnt_slot * 32 + lane] = first_len;
             } else if (ul >= 0) {
@@ -550,7 +568,7 @@ __global__ void __launch_bounds__(TILE_THREADS, TILE_MIN_CTAS) decode_tile_kerne
             }
           } else {
             // ArrayType(String/Binary): two offset levels -> ragged or count mode (never uniform)
-            if (A.uniform_len[fd->var_slot] == TILE_RAGGED) {
+            if (RG && A.uniform_len[fd->var_slot] == TILE_RAGGED) {
               rg_src[fd->var_slot * 32 + lane] = body;
               rg_cnt[fd->cnt_slot * 32 + lane] = n;
               rg_cnt[(fd->cnt_slot + 1) * 32 + lane] = total;
@@ -618,7 +636,7 @@ __global__ void __launch_bounds__(TILE_THREADS, TILE_MIN_CTAS) decode_tile_kerne
             }
           } else {
             const int32_t ul = A.uniform_len[fd->var_slot];
-            if (ul == TILE_RAGGED) {
+            if (RG && ul == TILE_RAGGED) {
               rg_src[fd->var_slot * 32 + lane] = pk;
               rg_cnt[fd->cnt_slot * 32 + lane] = n;
             } else if (ul >= 0) {
@@ -671,7 +689,7 @@ __global__ void __launch_bounds__(TILE_THREADS, TILE_MIN_CTAS) decode_tile_kerne
         --skip;
       }
       if (bad || p >= fl_end) break;
-      skip = TILE_PARSE_WARPS - 1;                           // the entry this warp owns
+      skip = PW - 1;                           // the entry this warp owns
       uint32_t elen, klen, vlen;
       if (T.u8(p) != 0x0A) { bad = true; break; }
       ++p;
@@ -781,81 +799,99 @@ __global__ void __launch_bounds__(TILE_THREADS, TILE_MIN_CTAS) decode_tile_kerne
       if (w4[k] && (atomicOr(&sseen[lane * 4 + k], w4[k]) & w4[k])) bad = true;
     if (bad) atomicOr(&sseen[160], 1u << lane);            // this row goes to the general path whatever else happens to it
   }
-  asm volatile("bar.sync 1, %0;" ::"r"(TILE_PARSE_WARPS * 32) : "memory");
-  if (A.ragged) {
+  asm volatile("bar.sync 1, %0;" ::"r"(PW * 32) : "memory");
+  if (RG) {
     // ================= ragged columns, finished in this pass =================
-    // (T) tile-local exclusive prefix of every count array over the 32 rows (lane = row); array a by warp a % W
-    for (uint32_t a = wid; a < A.n_cnt; a += TILE_PARSE_WARPS) {
+    // (T) tile-local exclusive prefix of every count array over the 32 rows (lane = row); array a by warp a % W.  The tile's
+    //     totals go out to the look-back table right away.
+    const uint32_t nc = A.n_cnt, nc4 = (nc + 3u) & ~3u;                            // table rows are padded to whole uint4
+    const uint32_t ptid = threadIdx.x;                                              // 0 .. W*32-1 (parse warps come first)
+    for (uint32_t a = wid; a < nc; a += PW) {
       const uint32_t c = rg_cnt[a * 32 + lane];
       uint32_t tot;
       const uint32_t ex = warp_excl_scan_u32(c, tot);
       rg_cnt[a * 32 + lane] = ex;
-      if (lane == 0) rg_tot[a] = tot;
+      if (lane == 0) { rg_tot[a] = tot; rg_base[a] = 0ull; A.lb_agg[(size_t)tile * nc4 + a] = tot; }
     }
-    asm volatile("bar.sync 1, %0;" ::"r"(TILE_PARSE_WARPS * 32) : "memory");
-    // (L) bases across tiles: warp 0 publishes this tile's totals, then looks back over its predecessors' totals until it
-    //     meets one whose inclusive prefix is known (decoupled look-back, one flag per tile, lane = array when summing)
-    if (wid == 0) {
-      const uint32_t nc = A.n_cnt;
-      for (uint32_t a = lane; a < nc; a += 32) A.lb_agg[(size_t)tile * nc + a] = rg_tot[a];
-      __threadfence();
-      __syncwarp();
-      if (lane == 0) st_release_u32(&A.lb_flag[tile], 1u);
-      unsigned long long run[4] = {0ull, 0ull, 0ull, 0ull};                     // arrays lane, lane+32, lane+64, lane+96 (n_cnt <= 128)
-      bool give_up = false;
+    asm volatile("bar.sync 1, %0;" ::"r"(PW * 32) : "memory");
+    if (ptid == 0) { __threadfence(); st_release_u32(&A.lb_flag[tile], 1u); }
+    // (L) bases across tiles (decoupled look-back).  All parse warps look at once: thread j reads the flag of tile p - j
+    //     (W*32 predecessors per round), the warps agree through shared memory on the nearest predecessor whose inclusive
+    //     prefix is known (G_pre) and on whether every tile in front of it has published its totals; then the W*32 threads
+    //     share the (tile, four arrays) loads -- one L2 round trip whatever the number of arrays -- and add them into the
+    //     tile's bases with shared-memory atomics.
+    {
+      uint32_t* lbs = rg_tile + 2;                                                  // [W] per-warp summary: first prefix | first empty << 8
       int32_t p = (int32_t)tile - 1;
       uint32_t spins = 0;
+      bool give_up = false;
       while (p >= 0) {
-        const int32_t q = p - (int32_t)lane;                                     // lane k looks at tile p - k
-        const uint32_t fl = q >= 0 ? ld_acquire_u32(&A.lb_flag[q]) : 2u;         // in front of tile 0: prefix 0
-        const uint32_t pre_mask = __ballot_sync(FULLMASK, fl == 2u);
-        const uint32_t first_pre = pre_mask ? (uint32_t)__ffs((int)pre_mask) - 1u : 32u;
-        const uint32_t need = first_pre >= 31u ? 0xffffffffu : (2u << first_pre) - 1u;   // lanes 0 .. first_pre
-        if (__ballot_sync(FULLMASK, fl == 0u) & need) {                          // a predecessor has not published yet
-          // the batch is being abandoned (another tile raised the fallback flag), or something is badly wrong: never hang
-          if ((++spins & 63u) == 0u && ((ld_cg_u32(A.flags) & TF_FALLBACK) || spins > (1u << 24))) { give_up = true; break; }
-          __nanosleep(40);
+        const int32_t q = p - (int32_t)ptid;
+        const uint32_t fl = q >= 0 ? ld_acquire_u32(&A.lb_flag[q]) : 2u;            // in front of tile 0: prefix 0
+        const uint32_t pre_mask = __ballot_sync(FULLMASK, fl == 2u), emp_mask = __ballot_sync(FULLMASK, fl == 0u);
+        if (lane == 0) lbs[wid] = (pre_mask ? (uint32_t)__ffs((int)pre_mask) - 1u : 32u) | ((emp_mask ? (uint32_t)__ffs((int)emp_mask) - 1u : 32u) << 8);
+        asm volatile("bar.sync 1, %0;" ::"r"(PW * 32) : "memory");
+        // nearest known prefix / nearest unpublished tile over all windows: lane w reads warp w's summary, two warp reductions
+        const uint32_t sx = lane < PW ? lbs[lane] : 0x2020u;
+        const uint32_t g_pre = __reduce_min_sync(FULLMASK, (sx & 0xffu) < 32u ? 32u * lane + (sx & 0xffu) : 0xffffu);
+        const uint32_t g_emp = __reduce_min_sync(FULLMASK, (sx >> 8) < 32u ? 32u * lane + (sx >> 8) : 0xffffu);
+        const uint32_t span = min(g_pre, (uint32_t)(PW * 32 - 1));    // predecessors p .. p - span are needed
+        if (g_emp <= span) {                                                        // one of them has not published yet
+          // never hang: the batch may have been abandoned (another tile raised the fallback flag)
+          ++spins;
+          if (ptid == 0 && (spins & 31u) == 0u && ((ld_cg_u32(A.flags) & TF_FALLBACK) || spins > (1u << 22))) lbs[PW] = 1u;
+          asm volatile("bar.sync 1, %0;" ::"r"(PW * 32) : "memory");  // everybody has read lbs before it is rewritten
+          if (lbs[PW]) { give_up = true; break; }                    // one thread decides, all follow: the barriers stay matched
+          __nanosleep(100);
           continue;
         }
-        __threadfence();
-        const uint32_t kmax = min(first_pre, 31u);
-        for (uint32_t k = 0; k <= kmax; ++k) {
-          const int32_t t2 = p - (int32_t)k;
-          if (t2 < 0) break;
-          const bool is_pre = k == first_pre;
+        // (the flags were read with acquire loads at GPU scope and the values are read from L2: no further fence)
+        // unit = (four arrays, 32 predecessors): lane = predecessor, one 16-byte load each, one warp reduction (REDUX) per
+        // array, one shared-memory atomic per array and unit; the predecessor whose inclusive prefix is known adds its own
+        const uint32_t chunks = nc4 >> 2, groups = (span >> 5) + 1u;
+        for (uint32_t u = wid; u < chunks * groups; u += PW) {
+          const uint32_t c4 = (u % chunks) * 4u, g = (u / chunks) * 32u + lane;
+          const int32_t t2 = p - (int32_t)g;
+          uint4 v = make_uint4(0u, 0u, 0u, 0u);
+          if (g < g_pre && g <= span && t2 >= 0)
+            asm volatile("ld.global.cg.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(A.lb_agg + (size_t)t2 * nc4 + c4) : "memory");
+          else if (g == g_pre && t2 >= 0) {
+            const unsigned long long* r = A.lb_pre + (size_t)t2 * nc4 + c4;
 #pragma unroll
-          for (uint32_t j = 0; j < 4; ++j) {
-            const uint32_t a = lane + 32u * j;
-            if (a < nc) run[j] += is_pre ? ld_cg_u64(&A.lb_pre[(size_t)t2 * nc + a]) : (unsigned long long)ld_cg_u32(&A.lb_agg[(size_t)t2 * nc + a]);
+            for (uint32_t j = 0; j < 4; ++j) if (c4 + j < nc) { const unsigned long long x = ld_cg_u64(r + j); if (x) atomicAdd(&rg_base[c4 + j], x); }
+          }
+          const uint32_t s0 = __reduce_add_sync(FULLMASK, v.x), s1 = __reduce_add_sync(FULLMASK, v.y), s2 = __reduce_add_sync(FULLMASK, v.z), s3 = __reduce_add_sync(FULLMASK, v.w);
+          if (lane == 0) {                                                          // (32 tiles x < 2^26 bytes each: no overflow)
+            if (s0) atomicAdd(&rg_base[c4], (unsigned long long)s0);
+            if (s1) atomicAdd(&rg_base[c4 + 1], (unsigned long long)s1);
+            if (s2) atomicAdd(&rg_base[c4 + 2], (unsigned long long)s2);
+            if (s3) atomicAdd(&rg_base[c4 + 3], (unsigned long long)s3);
           }
         }
-        if (first_pre < 32u) break;
-        p -= 32;
+        asm volatile("bar.sync 1, %0;" ::"r"(PW * 32) : "memory");
+        if (g_pre < (uint32_t)(PW * 32)) break;
+        p -= PW * 32;
       }
-      bool over = false;
-#pragma unroll
-      for (uint32_t j = 0; j < 4; ++j) {
-        const uint32_t a = lane + 32u * j;
-        if (a < nc) {
-          const unsigned long long incl = run[j] + rg_tot[a];
-          rg_base[a] = run[j];
-          A.lb_pre[(size_t)tile * nc + a] = incl;
-          if (incl > A.cap[a] || incl > 0x7fffffffull) over = true;             // target buffer (or int32 offsets) too small: host redoes the batch
-          if (row0 + TILE_ROWS >= n_rows) A.totals[a] = incl;                    // the last tile knows the grand totals
+      // this tile's inclusive prefixes: published by warp 0; capacity / int32 checks
+      if (wid == 0) {
+        bool over = false;
+        for (uint32_t a = lane; a < nc; a += 32) {
+          const unsigned long long incl = rg_base[a] + rg_tot[a];
+          A.lb_pre[(size_t)tile * nc4 + a] = incl;
+          if (incl > A.cap[a] || incl > 0x7fffffffull) over = true;                 // target buffer (or int32 offsets) too small: the host redoes the batch
+          if (row0 + TILE_ROWS >= n_rows) A.totals[a] = incl;                        // the last tile knows the grand totals
         }
-      }
-      __threadfence();
-      __syncwarp();
-      if (lane == 0) st_release_u32(&A.lb_flag[tile], 2u);
-      over = __any_sync(FULLMASK, over);
-      if (give_up || over) {
-        if (lane == 0) { rg_tile[1] = 1u; atomicOr(A.flags, over ? (TF_OVERFLOW | TF_FALLBACK) : TF_FALLBACK); }
+        __threadfence();
+        __syncwarp();
+        if (lane == 0) st_release_u32(&A.lb_flag[tile], 2u);
+        over = __any_sync(FULLMASK, over);
+        if ((give_up || over) && lane == 0) { rg_tile[1] = 1u; atomicOr(A.flags, over ? (TF_OVERFLOW | TF_FALLBACK) : TF_FALLBACK); }
       }
     }
-    asm volatile("bar.sync 1, %0;" ::"r"(TILE_PARSE_WARPS * 32) : "memory");
+    asm volatile("bar.sync 1, %0;" ::"r"(PW * 32) : "memory");
     // (C) offsets + values: column v by warp v % W, lane = row.  Cells of consecutive rows are adjacent in the output.
     if (!rg_tile[1]) {
-      for (uint32_t v = wid; v < (uint32_t)A.sch.n_var; v += TILE_PARSE_WARPS) {
+      for (uint32_t v = wid; v < (uint32_t)A.sch.n_var; v += PW) {
         if (A.uniform_len[v] != TILE_RAGGED) continue;
         const DevField& fd = sfields[A.var_field[v]];
         const uint32_t a0 = (uint32_t)fd.cnt_slot;
@@ -910,7 +946,7 @@ __global__ void __launch_bounds__(TILE_THREADS, TILE_MIN_CTAS) decode_tile_kerne
 #pragma unroll
     for (int k = 0; k < 4; ++k) all[k] = sseen[lane * 4 + k];
     const uint32_t act_mask = __ballot_sync(FULLMASK, active);
-    for (uint32_t f = wid; f < nf; f += TILE_PARSE_WARPS) {
+    for (uint32_t f = wid; f < nf; f += PW) {
       const uint32_t wsel = f < 32 ? all[0] : f < 64 ? all[1] : f < 96 ? all[2] : all[3];
       const bool present = (wsel >> (f & 31)) & 1;
       const uint32_t m = __ballot_sync(FULLMASK, present && active);

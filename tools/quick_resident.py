@@ -1,4 +1,5 @@
-"""quick device-resident timing of the pipelined decode (developer tool; bench.py is the measurement of record)"""
+"""quick device-resident timing of the pipelined decode (developer tool; bench.py is the measurement of record)
+usage: quick_resident.py MIB STEPS [cfg2|ragged|strings]"""
 import os, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
@@ -9,7 +10,24 @@ from spark_tfrecord_b200 import _native
 
 mib = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
 steps = int(sys.argv[2]) if len(sys.argv) > 2 else 200
-schema, n, dev, batches = bench.make_device_pool(mib, 2, seed=2024, device=0, keep_host=2)
+kind = sys.argv[3] if len(sys.argv) > 3 else "cfg2"
+if kind == "cfg2":
+    schema, n, dev, batches = bench.make_device_pool(mib, 2, seed=2024, device=0, keep_host=2)
+else:
+    if kind == "ragged":
+        n = bench.records_per_batch(mib)
+        mk = lambda seed: bench.cfg2_schema_and_columns(n, seed=seed, ragged_bytes=True)
+    else:
+        from oracle.corpus import cfg1_columns          # developer tool only: 4 long, 4 float, 2 string columns, ~220-byte records
+        n = (mib << 20) // 220
+        mk = lambda seed: cfg1_columns(n, seed=seed)
+    dev, batches = [], []
+    for i in range(2):
+        schema, cols = mk(100 + i)
+        enc = _native.Encoder(schema, 0, 0)
+        data = np.frombuffer(enc.encode(cols), dtype=np.uint8)
+        enc.close()
+        batches.append(data); dev.append(torch.from_numpy(data.copy()).cuda())
 dec = _native.Decoder(schema)
 for i in range(4):
     b, used = dec.decode(dev[i % 2]); assert b.info["error_code"] == 0; b.release()
@@ -33,7 +51,7 @@ for mode in ("submit", "decode"):
     wall = time.perf_counter() - t0
     ms = e0.elapsed_time(e1)
     prof = dec.get_profile()
-    print(mode, f"{tot / ms / 1e6:.1f} GB/s  {ms / steps:.4f} ms/step  wall {wall / steps * 1e3:.4f} ms/step",
+    print(kind, mode, f"{tot / ms / 1e6:.1f} GB/s  {ms / steps:.4f} ms/step  wall {wall / steps * 1e3:.4f} ms/step",
           {k: round(v / steps, 4) for k, v in prof["ms"].items()}, "launches/step", prof["launches"] / steps, dec.stats())
     dec.set_profiling(False)
 dec.close()
