@@ -60,6 +60,7 @@ def parse_args():
     ap.add_argument("--batches-per-step", type=int, default=64, help="batch decodes per step (cycling through the pool)")
     ap.add_argument("--e2e-batches-per-step", type=int, default=4, help="batch decodes per step of the host-buffer (e2e) measurement")
     ap.add_argument("--cpu-sample-mib", type=int, default=48, help="framed bytes each host thread decodes per pass (at most batch / threads)")
+    ap.add_argument("--cfg5-passes", type=int, default=4, help="passes over the 200 GB logical corpus in the configs[4] side measurement (0: skip)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-extra", action="store_true")
@@ -589,6 +590,58 @@ def run_extras(torch, dev, peak):
 
 
 # ---------------------------------------------------------------------------------------------
+# configs[4]: file-sharded decode of a 200 GB logical corpus, strong scaling over the ranks
+# ---------------------------------------------------------------------------------------------
+CFG5_FILES = 64
+CFG5_BLOCK = 768 << 20          # block size of the streaming reader: does not divide a file, so blocks end inside records
+
+
+def cfg5_file_sizes(pool_batches: int):
+    """64 files, sizes log-uniform in [0.5, 8] GiB rounded to whole pool batches (a file = consecutive whole 1 GiB batches of
+    this rank's pool, starting at batch (file index mod pool)): about 200 GB in total"""
+    rng = np.random.Generator(np.random.PCG64(5))
+    gib = np.exp(rng.uniform(np.log(0.5), np.log(8.0), CFG5_FILES))
+    return [int(min(8, max(1, round(x)))) for x in gib]
+
+
+def run_cfg5(torch, dec, d_batches, batch_bytes, rank, world, passes):
+    """Every rank takes the files shard_lpt assigns it (the reference's unit is the unsplittable file, M/DefaultSource.scala:26-29)
+    and streams each through tfr_decode_submit in blocks of at most 768 MiB: a block that ends inside a record is submitted as
+    non-final, its consumed-bytes count says where the next block starts (the carry-over of a streaming reader; the bytes are
+    already in HBM, so the carry is a pointer, and blocks start at any alignment).  Returns (bytes, device ms, files, blocks)."""
+    from spark_tfrecord_b200.sharding import shard_lpt
+    sizes = cfg5_file_sizes(len(d_batches))
+    nominal = [n * (1 << 30) for n in sizes]
+    mine = shard_lpt(nominal, world)[rank]
+    stream = torch.cuda.ExternalStream(dec.stream())
+    P = len(d_batches)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    tot, blocks = 0, 0
+    e0.record(stream)
+    for _ in range(passes):
+        for f in mine:
+            for k in range(sizes[f]):                       # the file's batches; a record never straddles two of them
+                t = d_batches[(f + k) % P]
+                nb = batch_bytes[(f + k) % P]
+                pos = 0
+                while pos < nb:
+                    take = min(CFG5_BLOCK, nb - pos)
+                    final_block = pos + take == nb
+                    b = dec.submit((t.data_ptr() + pos, take, 1), is_final=final_block and k == sizes[f] - 1)
+                    info = b.info                             # the reader needs consumed_bytes before it can cut the next block
+                    assert info["error_code"] == 0, info
+                    used = info["consumed_bytes"]
+                    assert used > 0 and (used == take or not final_block)
+                    b.release()
+                    pos += used
+                    tot += used
+                    blocks += 1
+    e1.record(stream)
+    torch.cuda.synchronize()
+    return tot, e0.elapsed_time(e1), len(mine), blocks, sizes
+
+
+# ---------------------------------------------------------------------------------------------
 # our arm
 # ---------------------------------------------------------------------------------------------
 def run_ours(args):
@@ -672,6 +725,36 @@ def run_ours(args):
     if not args.no_parity and rank == 0:
         parity = parity_check(dec, schema, d_batches[0], h_batches[0], max(1, host_cores()))
 
+    # ---------------- configs[4]: file-sharded strong scaling ----------------
+    cfg5 = None
+    if args.cfg5_passes > 0 and P >= 8:
+        barrier()
+        c_bytes, c_ms, c_files, c_blocks, c_sizes = run_cfg5(torch, dec, d_batches, batch_bytes, rank, world, args.cfg5_passes)
+        barrier()
+        cfg5 = (c_bytes, c_ms, c_files, c_blocks, c_sizes)
+
+    # ---------------- the one collective of this project: schema inference + NCCL reduce (N > 1) ----------------
+    infer = None
+    if use_dist:
+        from spark_tfrecord_b200.sharding import allreduce_schema
+        inf = _native.Infer(0, dev)
+        nb_inf = min(batch_bytes[0], 64 << 20)
+        # a record-aligned prefix: non-final block, the consumed count is where the last whole record ends
+        barrier()
+        t0 = time.perf_counter()
+        used = inf.update_block((d_batches[0].data_ptr(), nb_inf, 1), is_final=False)
+        local = inf.result()
+        t_scan = time.perf_counter() - t0
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        merged = allreduce_schema(local, dist, f"cuda:{dev}")
+        torch.cuda.synchronize()
+        t_reduce = time.perf_counter() - t0
+        assert len(merged) == 64 and used > 0, (len(merged), used)
+        infer = {"names": len(merged), "scan_bytes_per_rank": int(used), "scan_ms": 1e3 * t_scan, "allreduce_ms": 1e3 * t_reduce,
+                 "collective": "all_gather_object(names) + 2 x all_reduce(MAX) over NCCL"}
+        inf.close()
+
     # ---------------- end to end: pinned host -> device -> pinned host, one handle, one thread ----------------
     e2e = None
     if not args.no_e2e:
@@ -725,14 +808,15 @@ def run_ours(args):
 
     # ---------------- reduce over ranks ----------------
     if use_dist:
-        t = torch.tensor([ms, t_wall, e2e[1] if e2e else 0.0], dtype=torch.float64, device=f"cuda:{dev}")
+        t = torch.tensor([ms, t_wall, e2e[1] if e2e else 0.0, cfg5[1] if cfg5 else 0.0], dtype=torch.float64, device=f"cuda:{dev}")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        s = torch.tensor([float(in_bytes), float(e2e[0] if e2e else 0)], dtype=torch.float64, device=f"cuda:{dev}")
+        s = torch.tensor([float(in_bytes), float(e2e[0] if e2e else 0), float(cfg5[0] if cfg5 else 0), float(cfg5[3] if cfg5 else 0)], dtype=torch.float64, device=f"cuda:{dev}")
         dist.all_reduce(s, op=dist.ReduceOp.SUM)
-        ms, t_wall, t_e2e_max = t.tolist()
-        tot_in, tot_e2e = s.tolist()
+        ms, t_wall, t_e2e_max, cfg5_ms_max = t.tolist()
+        tot_in, tot_e2e, cfg5_bytes, cfg5_blocks = s.tolist()
     else:
         tot_in, tot_e2e, t_e2e_max = float(in_bytes), float(e2e[0] if e2e else 0), (e2e[1] if e2e else 0.0)
+        cfg5_ms_max, cfg5_bytes, cfg5_blocks = (cfg5[1], float(cfg5[0]), float(cfg5[3])) if cfg5 else (0.0, 0.0, 0.0)
 
     if rank != 0:
         if use_dist:
@@ -789,6 +873,18 @@ def run_ours(args):
     }
     if parity:
         line["parity_checked"] = parity
+    if infer:
+        line["schema_inference_reduce"] = infer
+    if cfg5:
+        corpus = sum(cfg5[4]) * (1 << 30)
+        line["cfg5_file_sharded"] = {
+            "workload": f"configs[4]: {CFG5_FILES} files of configs[1] records, sizes log-uniform 0.5-8 GiB ({corpus / 1e9:.0f} GB logical corpus), assigned to the "
+                        f"{world} rank(s) by LPT on their sizes (the file is the reference's unsplittable unit), each streamed in blocks of <= 768 MiB with carry-over",
+            "value": cfg5_bytes / (cfg5_ms_max * 1e-3) / 1e9, "unit": UNIT, "scaling": "strong", "passes_over_corpus": args.cfg5_passes,
+            "framed_bytes_decoded": int(cfg5_bytes), "blocks": int(cfg5_blocks), "device_ms_max_over_ranks": cfg5_ms_max,
+            "replay": f"each rank's files replay its {P} resident 1 GiB batches ({P * batch_bytes[0] / 1e9:.0f} GB unique per GPU); the logical corpus is decoded {args.cfg5_passes}x",
+            "note": "every block waits for its consumed-bytes count before the next is cut (one host round trip per block), so the frame index of block t+1 "
+                    "does not overlap the decode of block t as it does in the headline loop"}
     if e2e:
         eb = args.e2e_batches_per_step
         line["e2e"] = {"value": tot_e2e / t_e2e_max / 1e9, "unit": UNIT, "h2d_bytes_per_step": int(batch_bytes[0]) * eb,

@@ -63,6 +63,7 @@ struct TileArgs {
   const uint8_t* data;          // framed bytes, any alignment
   uint32_t nbytes;
   uint32_t misalign;            // data & 15
+  uint32_t pf_dist;             // L2 prefetch distance in tiles (CTAs resident on the whole GPU), 0: off
   const uint32_t* rec_off;      // [n+1]
   uint32_t n;                   // rows in the batch = stride of the scratch arrays; with n_dev: the CAPACITY the host sized everything for
   const uint32_t* n_dev;        // non-null: the number of rows is read here (FrameResult::n_records of this batch, still on the device when the
@@ -389,6 +390,17 @@ __global__ void __launch_bounds__((PW + CW) * 32, (PW >= 12 ? TILE_MIN_CTAS : 8)
       uint32_t c = scrc[lane];
       for (uint32_t o = b0 + 16 * K; o < end; ++o) c = crc_byte(s8, c, T.u8(o));
       if (crc_mask(~c) != t_u32(T, end)) atomicOr(A.flags, TF_FALLBACK);        // the general path reports the error at the right record
+    }
+    if (cw == CW - 1 && A.pf_dist) {
+      // The tile that will take this CTA's place when it retires (tiles start in index order, pf_dist = resident CTAs of the
+      // whole GPU): ask L2 for its records now, so that its bulk copies find them there instead of in DRAM.  A tile spends
+      // its first microseconds waiting for those copies with its shared memory allocated and idle.
+      const uint32_t row2 = (tile + A.pf_dist) * TILE_ROWS + lane;
+      if (row2 < n_rows) {
+        const uint32_t o2 = A.rec_off[row2] + mis, e2 = min(A.rec_off[row2 + 1] + mis, lim & ~15u);
+        const uint32_t a2 = (o2 + 15u) & ~15u;
+        if (e2 > a2 + 16u) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(base + a2), "r"((e2 - a2) & ~15u) : "memory");
+      }
     }
     return;
   }
