@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 #include <nvtx3/nvToolsExt.h>      // header-only NVTX 3: ranges show up in Nsight Systems / ncu --nvtx, cost nothing when no tool is attached
 #include <algorithm>
+#include <cmath>
 #include <atomic>
 #include <cstdio>
 #include <cstdlib>

@@ -253,6 +253,7 @@ __host__ __device__ inline uint32_t tile_schema_smem(uint32_t nf, uint32_t names
 __host__ __device__ inline uint32_t tile_const_bytes(uint32_t nf, uint32_t names_bytes) { return TILE_CRC_BYTES + TILE_SEEN_BYTES + tile_schema_smem(nf, names_bytes); }
 // ragged mode scratch behind the tile: cell source offsets [n_var][32] | per-array counts -> local offsets [n_cnt][32] | totals [n_cnt] | bases u64 [n_cnt] | tile id
 __host__ __device__ inline uint32_t tile_ragged_bytes(uint32_t n_var, uint32_t n_cnt) { return (n_var + n_cnt) * 128u + n_cnt * 4u + n_cnt * 8u + 16u + 16u + 64u; }
+__host__ __device__ inline uint32_t tile_seq_bytes(uint32_t n_var) { return n_var * 256u + 16u; }      // SequenceExample: FeatureList count sums
 __host__ __device__ inline uint32_t tile_smem_bytes(uint32_t nf, uint32_t names_bytes, uint32_t tile_cap, uint32_t ragged_bytes = 0) {
   return 16 + tile_const_bytes(nf, names_bytes) + tile_cap + 64 + ragged_bytes;   // +64: template compares may look a few bytes past the tile
 }
@@ -283,6 +284,9 @@ __global__ void __launch_bounds__((PW + CW) * 32, (PW >= 12 ? TILE_MIN_CTAS : 8)
   uint32_t* rg_tot = rg_cnt + A.n_cnt * 32u;                                          // [n_cnt] tile totals
   unsigned long long* rg_base = reinterpret_cast<unsigned long long*>(rg_tot + ((A.n_cnt + 1u) & ~1u) + 16u);  // [n_cnt] exclusive bases of this tile
   uint32_t* rg_tile = rg_tot + ((A.n_cnt + 1u) & ~1u);                                // [0] tile id, [1] skip-copy flag, [2..14) look-back summaries of the warps
+  // SequenceExample: per (column, row) element / byte counts of the FeatureLists, summed over the parse warps [n_var][32][2]
+  uint32_t* sq_cnt = reinterpret_cast<uint32_t*>(tile_b + A.tile_cap + 64 + (RG ? tile_ragged_bytes((uint32_t)A.sch.n_var, A.n_cnt) : 0u));
+  if (SEQ) for (uint32_t i = threadIdx.x; i < (uint32_t)A.sch.n_var * 64u; i += (PW + CW) * 32) sq_cnt[i] = 0u;
   // Tile id.  Ragged mode: tiles look back at their predecessors' totals, so ids are handed out in start order (a tile only
   // ever waits for tiles that are already running); otherwise the block index.
   uint32_t tile = blockIdx.x;
@@ -534,6 +538,7 @@ __global__ void __launch_bounds__((PW + CW) * 32, (PW >= 12 ? TILE_MIN_CTAS : 8)
       if (kind == K_BYTES) {
         // BytesList: { 0A blen bytes }*
         uint32_t n = 0, first_off = 0, first_len = 0, first_data = 0, total = 0;
+        bool xcode = false;                                                   // a string of this cell is malformed UTF-8 (ragged columns only)
         const uint32_t body = p;
         const bool is_str = fd && fd->elem_type == TFR_T_STRING;
         while (p < eend) {
@@ -542,15 +547,20 @@ __global__ void __launch_bounds__((PW + CW) * 32, (PW >= 12 ? TILE_MIN_CTAS : 8)
           ++p;
           const uint32_t lp = p;
           if (!t_len(T, p, eend, bl) || eend - p < bl) { bad = true; break; }
+          uint32_t ol = bl;                                                   // bytes this element contributes to the column
           if (is_str) {
-            // StringType = Java UTF-8 decode/re-encode: identity for well-formed input; malformed input needs the
-            // U+FFFD transcode, which only the general path implements
+            // StringType = Java UTF-8 decode/re-encode: identity for well-formed input.  Malformed input becomes U+FFFD per
+            // malformed unit (java_utf8_transcode): a ragged column takes the re-encoded length here and the copy-out
+            // transcodes; a uniform or count-mode column leaves the row to the general path.
             uint32_t acc = 0;
             for (uint32_t i = 0; i < bl; ++i) acc |= T.u8(p + i);
-            if (acc >= 0x80 && !utf8_valid(T.b + p, bl)) { bad = true; break; }
+            if (acc >= 0x80 && !utf8_valid(T.b + p, bl)) {
+              if (RG && A.uniform_len[fd->var_slot] == TILE_RAGGED) { ol = java_utf8_transcode(T.b + p, bl, nullptr); xcode = true; }
+              else { bad = true; break; }
+            }
           }
-          if (n == 0) { first_off = lp + g0; first_len = bl; first_data = p; }
-          ++n; total += bl;
+          if (n == 0) { first_off = lp + g0; first_len = ol; first_data = p; }
+          ++n; total += ol;
           p += bl;
         }
         if (bad) break;
@@ -559,7 +569,8 @@ __global__ void __launch_bounds__((PW + CW) * 32, (PW >= 12 ? TILE_MIN_CTAS : 8)
             if (n == 0) { bad = true; break; }                                  // .head of an empty list: error path
             const int32_t ul = A.uniform_len[fd->var_slot];
             if (RG && ul == TILE_RAGGED) {
-              rg_src[fd->var_slot * 32 + lane] = first_data;
+              // (a malformed string: the copy-out re-reads the raw length from the varint in front of the data)
+              rg_src[fd->var_slot * 32 + lane] = first_data | (xcode ? 0x80000000u : 0u);
               rg_cnt[fd->cnt_slot * 32 + lane] = first_len;
             } else if (ul >= 0) {
               if ((uint32_t)ul != first_len) shape_bad = 1;
@@ -581,7 +592,7 @@ __global__ void __launch_bounds__((PW + CW) * 32, (PW >= 12 ? TILE_MIN_CTAS : 8)
           } else {
             // ArrayType(String/Binary): two offset levels -> ragged or count mode (never uniform)
             if (RG && A.uniform_len[fd->var_slot] == TILE_RAGGED) {
-              rg_src[fd->var_slot * 32 + lane] = body;
+              rg_src[fd->var_slot * 32 + lane] = body | (xcode ? 0x80000000u : 0u);
               rg_cnt[fd->cnt_slot * 32 + lane] = n;
               rg_cnt[(fd->cnt_slot + 1) * 32 + lane] = total;
             } else {
@@ -688,20 +699,15 @@ __global__ void __launch_bounds__((PW + CW) * 32, (PW >= 12 ? TILE_MIN_CTAS : 8)
     }
     if (p != cend) bad = true;
     // ---- SequenceExample.feature_lists: { 0A elen 0A klen key 12 vlen FeatureList }*, FeatureList = { 0A flen Feature }* ----
+    // A SequenceExample typically has few FeatureLists with many steps each: handing whole entries to warps would leave most
+    // of the tile's warps idle behind the one that walks a 64-step list.  Every parse warp therefore walks EVERY entry's
+    // header and step chain (`0A flen` hops), but fully parses only the steps s with s % W == its index; element and byte
+    // counts are summed per (row, column) in shared memory and written out after the parse barrier.  The entry's owner
+    // (entry index % W, continuing the count of the context entries) does the per-entry bookkeeping.
     p = fl_start;
     while (SEQ && !bad && p < fl_end) {
-      while (skip && p < fl_end) {
-        const uint32_t b1 = T.u8(p + 1);
-        if (b1 < 0x80) p += 2 + b1;
-        else {
-          uint32_t q = p + 1, el;
-          if (!t_len(T, q, fl_end, el)) { bad = true; break; }
-          p = q + el;
-        }
-        --skip;
-      }
-      if (bad || p >= fl_end) break;
-      skip = PW - 1;                           // the entry this warp owns
+      const bool owner = skip == 0;
+      skip = owner ? PW - 1 : skip - 1;
       uint32_t elen, klen, vlen;
       if (T.u8(p) != 0x0A) { bad = true; break; }
       ++p;
@@ -716,9 +722,11 @@ __global__ void __launch_bounds__((PW + CW) * 32, (PW >= 12 ? TILE_MIN_CTAS : 8)
       if (p >= eend || T.u8(p) != 0x12) { bad = true; break; }
       ++p;
       if (!t_len(T, p, eend, vlen) || p + vlen != eend) { bad = true; break; }
-      uint32_t hi = 0;
-      for (uint32_t i = 0; i < klen; ++i) hi |= T.u8(key + i);
-      if (hi >= 0x80 && !utf8_valid(T.b + key, klen)) { bad = true; break; }
+      if (owner) {
+        uint32_t hi = 0;
+        for (uint32_t i = 0; i < klen; ++i) hi |= T.u8(key + i);
+        if (hi >= 0x80 && !utf8_valid(T.b + key, klen)) { bad = true; break; }
+      }
       int f = -1;
       {
         uint32_t h = name_hash(T.b + key, klen);
@@ -739,10 +747,12 @@ __global__ void __launch_bounds__((PW + CW) * 32, (PW >= 12 ? TILE_MIN_CTAS : 8)
       const DevField* fd = f >= 0 ? &sfields[f] : nullptr;
       if (fd) {
         if (fd->depth != 2) { bad = true; break; }            // array of heads / scalar from a FeatureList: general path
-        unsigned long long bit = 1ull << (f & 63);
-        // a name present in context AND feature_lists (context wins) or twice here: general path
-        if (f < 64) { if (seen_lo & bit) { bad = true; break; } seen_lo |= bit; }
-        else { if (seen_hi & bit) { bad = true; break; } seen_hi |= bit; }
+        if (owner) {
+          unsigned long long bit = 1ull << (f & 63);
+          // a name present in context AND feature_lists (context wins) or twice here: general path
+          if (f < 64) { if (seen_lo & bit) { bad = true; break; } seen_lo |= bit; }
+          else { if (seen_hi & bit) { bad = true; break; } seen_hi |= bit; }
+        }
       }
       uint32_t steps = 0, tot_n = 0, tot_bytes = 0;
       while (p < eend) {                                      // steps
@@ -751,7 +761,9 @@ __global__ void __launch_bounds__((PW + CW) * 32, (PW >= 12 ? TILE_MIN_CTAS : 8)
         ++p;
         if (!t_len(T, p, eend, flen) || eend - p < flen) { bad = true; break; }
         const uint32_t fend = p + flen;
+        const bool mine = steps % PW == wid;                  // this warp parses the step; the others only hop over it
         ++steps;
+        if (!mine) { p = fend; continue; }
         if (flen == 0) { if (fd) bad = true; continue; }     // kind not set: an error if the schema wants the column
         uint32_t kt = T.u8(p++), llen;
         uint32_t kind = kt == 0x0A ? K_BYTES : kt == 0x12 ? K_FLOAT : kt == 0x1A ? K_INT64 : K_NONE;
@@ -793,11 +805,13 @@ __global__ void __launch_bounds__((PW + CW) * 32, (PW >= 12 ? TILE_MIN_CTAS : 8)
       }
       if (bad) break;
       if (fd) {
-        A.cnt[(size_t)fd->cnt_slot * A.n + row] = steps;
-        A.cnt[(size_t)(fd->cnt_slot + 1) * A.n + row] = tot_n;
-        if (fd->n_levels == 3) A.cnt[(size_t)(fd->cnt_slot + 2) * A.n + row] = tot_bytes;
-        A.src[(size_t)fd->var_slot * A.n + row] = entry_pos + g0;
-        A.cflag[(size_t)fd->var_slot * A.n + row] = CF_FLIST;
+        if (tot_n) atomicAdd(&sq_cnt[(fd->var_slot * 32 + lane) * 2], tot_n);
+        if (tot_bytes) atomicAdd(&sq_cnt[(fd->var_slot * 32 + lane) * 2 + 1], tot_bytes);
+        if (owner) {
+          A.cnt[(size_t)fd->cnt_slot * A.n + row] = steps;
+          A.src[(size_t)fd->var_slot * A.n + row] = entry_pos + g0;
+          A.cflag[(size_t)fd->var_slot * A.n + row] = CF_FLIST;
+        }
       }
       p = eend;
     }
@@ -916,10 +930,20 @@ __global__ void __launch_bounds__((PW + CW) * 32, (PW >= 12 ? TILE_MIN_CTAS : 8)
         o0[row] = (int32_t)(b0 + ex0);
         if (last_row) o0[n_rows] = (int32_t)(b0 + ex0 + c0);
         if (c0 == 0) { if (last_row && fd.n_levels == 2) A.offs[v * 3 + 1][b0 + ex0] = (int32_t)(rg_base[a0 + 1] + rg_cnt[(a0 + 1) * 32 + lane]); continue; }
-        const uint32_t src = rg_src[v * 32 + lane];
+        const uint32_t src = rg_src[v * 32 + lane] & 0x7fffffffu;
+        const bool xcode = rg_src[v * 32 + lane] >> 31;          // a malformed UTF-8 string in this cell: re-encode instead of copy
         uint8_t* vals = reinterpret_cast<uint8_t*>(A.var_values[v]);
         if (fd.depth == 0) {                                   // scalar string / binary: c0 bytes
-          t_copy_out(T, src, vals + b0 + ex0, c0);
+          if (xcode) {
+            // raw length: the varint that ends right in front of the data (its last byte has the top bit clear, the ones before
+            // it set; the tag 0A in front of it has it clear again)
+            uint32_t k = 1;
+            while (k < 5 && (T.u8(src - 1 - k) & 0x80u)) ++k;
+            uint32_t q = src - k, raw = 0;
+            t_len(T, q, src, raw);
+            java_utf8_transcode(T.b + src, raw, vals + b0 + ex0);
+          }
+          else t_copy_out(T, src, vals + b0 + ex0, c0);
         } else if (fd.kind == K_FLOAT) {                       // packed floats
           if (fd.elem_type == TFR_T_FLOAT32) { uint32_t* d = reinterpret_cast<uint32_t*>(vals) + b0 + ex0; for (uint32_t i = 0; i < c0; ++i) d[i] = t_u32(T, src + 4 * i); }
           else { double* d = reinterpret_cast<double*>(vals) + b0 + ex0; for (uint32_t i = 0; i < c0; ++i) d[i] = (double)__uint_as_float(t_u32(T, src + 4 * i)); }
@@ -942,8 +966,9 @@ __global__ void __launch_bounds__((PW + CW) * 32, (PW >= 12 ? TILE_MIN_CTAS : 8)
             t_len(T, qq, q + 5, bl);
             q = qq;
             o1[b0 + ex0 + i] = (int32_t)vpos;
-            t_copy_out(T, q, vals + vpos, bl);
-            vpos += bl; q += bl;
+            if (xcode && !all_ascii(T.b + q, bl) && !utf8_valid(T.b + q, bl)) vpos += java_utf8_transcode(T.b + q, bl, vals + vpos);
+            else { t_copy_out(T, q, vals + vpos, bl); vpos += bl; }
+            q += bl;
           }
           if (last_row) o1[b0 + ex0 + c0] = (int32_t)vpos;
         }
@@ -962,6 +987,11 @@ __global__ void __launch_bounds__((PW + CW) * 32, (PW >= 12 ? TILE_MIN_CTAS : 8)
       const uint32_t wsel = f < 32 ? all[0] : f < 64 ? all[1] : f < 96 ? all[2] : all[3];
       const bool present = (wsel >> (f & 31)) & 1;
       const uint32_t m = __ballot_sync(FULLMASK, present && active);
+      if (SEQ && active && present && sfields[f].depth == 2 && A.cnt) {      // FeatureList column: the warps' partial counts
+        const DevField& fd = sfields[f];
+        A.cnt[(size_t)(fd.cnt_slot + 1) * A.n + row] = sq_cnt[(fd.var_slot * 32 + lane) * 2];
+        if (fd.n_levels == 3) A.cnt[(size_t)(fd.cnt_slot + 2) * A.n + row] = sq_cnt[(fd.var_slot * 32 + lane) * 2 + 1];
+      }
       if (active && !present && sfields[f].elem_type != TFR_T_NULL) {
         const DevField& fd = sfields[f];
         if (!fd.nullable) bad = true;                                         // NullPointerException: error path

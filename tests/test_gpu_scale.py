@@ -423,3 +423,42 @@ def test_ragged_bytes_cfg2_steady_state(native, oracle):
         assert dec.stats()["speculative_redone"] == 1
     finally:
         dec.close()
+
+
+def test_malformed_utf8_in_ragged_string_columns_is_not_a_cliff(native, oracle):
+    """StringType cells with malformed UTF-8 (Java re-encodes them with U+FFFD, M/TFRecordDeserializer.scala:91,215) in ragged
+    columns are handled inside the single-pass kernel: same bytes as the oracle, no redo of the batch"""
+    from oracle.corpus import mixed_columns
+    from spark_tfrecord_b200._cabi import HostColumn
+    sch, cols = mixed_columns(20000, seed=9)
+    names = sch.names
+    rng = np.random.default_rng(3)
+    bad_seqs = [b"\xff", b"\xc3", b"\xe2\x82", b"\xed\xa0\x80", b"\xf0\x9f\x98", b"\xc0\xaf", b"ok\x80ok", b"\xf5\x80\x80\x80"]
+
+    def poison(col, every):
+        data = col.values.copy()
+        so = col.offsets[-1]
+        k = 0
+        for i in range(0, len(so) - 1, every):
+            a, b = int(so[i]), int(so[i + 1])
+            seq = bad_seqs[k % len(bad_seqs)]; k += 1
+            if b - a >= len(seq):
+                data[a:a + len(seq)] = np.frombuffer(seq, np.uint8)
+        return HostColumn(col.elem_type, col.depth, col.n_rows, col.validity, col.offsets, data)
+
+    clean = _encode(oracle, sch, cols)
+    cols2 = list(cols)
+    cols2[names.index("s")] = poison(cols[names.index("s")], 97)
+    cols2[names.index("as")] = poison(cols[names.index("as")], 53)
+    dirty = _encode(oracle, sch, cols2)
+    want = oracle.decode(dirty, sch)
+    assert not np.array_equal(want.columns[names.index("s")].values, cols2[names.index("s")].values)      # something was re-encoded
+    dec = native.Decoder(sch)
+    try:
+        b, _ = dec.decode(clean); b.release()
+        s0 = dec.stats()
+        b = dec.submit(dirty); _check_batch(oracle, b, dirty, sch, what="malformed UTF-8 in ragged string columns"); b.release()
+        s1 = dec.stats()
+        assert s1["speculative_submits"] == s0["speculative_submits"] + 1 and s1["speculative_redone"] == s0["speculative_redone"], (s0, s1)
+    finally:
+        dec.close()

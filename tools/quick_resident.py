@@ -17,6 +17,10 @@ else:
     if kind == "ragged":
         n = bench.records_per_batch(mib)
         mk = lambda seed: bench.cfg2_schema_and_columns(n, seed=seed, ragged_bytes=True)
+    elif kind == "seq":
+        from oracle.corpus import cfg4_columns          # developer tool only
+        n = (mib << 20) // 1650
+        mk = lambda seed: cfg4_columns(n, seed=seed)
     else:
         from oracle.corpus import cfg1_columns          # developer tool only: 4 long, 4 float, 2 string columns, ~220-byte records
         n = (mib << 20) // 220
@@ -24,11 +28,11 @@ else:
     dev, batches = [], []
     for i in range(2):
         schema, cols = mk(100 + i)
-        enc = _native.Encoder(schema, 0, 0)
+        enc = _native.Encoder(schema, 1 if kind == "seq" else 0, 0)
         data = np.frombuffer(enc.encode(cols), dtype=np.uint8)
         enc.close()
         batches.append(data); dev.append(torch.from_numpy(data.copy()).cuda())
-dec = _native.Decoder(schema)
+dec = _native.Decoder(schema, 1 if kind == "seq" else 0)
 for i in range(4):
     b, used = dec.decode(dev[i % 2]); assert b.info["error_code"] == 0; b.release()
 stream = torch.cuda.ExternalStream(dec.stream())
