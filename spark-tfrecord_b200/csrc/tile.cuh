@@ -253,7 +253,10 @@ __host__ __device__ inline uint32_t tile_schema_smem(uint32_t nf, uint32_t names
 __host__ __device__ inline uint32_t tile_const_bytes(uint32_t nf, uint32_t names_bytes) { return TILE_CRC_BYTES + TILE_SEEN_BYTES + tile_schema_smem(nf, names_bytes); }
 // ragged mode scratch behind the tile: cell source offsets [n_var][32] | per-array counts -> local offsets [n_cnt][32] | totals [n_cnt] | bases u64 [n_cnt] | tile id
 __host__ __device__ inline uint32_t tile_ragged_bytes(uint32_t n_var, uint32_t n_cnt) { return (n_var + n_cnt) * 128u + n_cnt * 4u + n_cnt * 8u + 16u + 16u + 64u; }
-__host__ __device__ inline uint32_t tile_seq_bytes(uint32_t n_var) { return n_var * 256u + 16u; }      // SequenceExample: FeatureList count sums
+#define TILE_SQ_STEPS 128u       // FeatureList steps per record the one-pass mode keeps per-step element counts for
+// SequenceExample scratch: FeatureList count sums [n_var][32][2] u32, then (one-pass mode, at most 4 variable-width columns)
+// the per-step element counts [n_var][TILE_SQ_STEPS][32] u8
+__host__ __device__ inline uint32_t tile_seq_bytes(uint32_t n_var, bool with_steps = false) { return n_var * 256u + 16u + (with_steps ? n_var * TILE_SQ_STEPS * 32u : 0u); }
 __host__ __device__ inline uint32_t tile_smem_bytes(uint32_t nf, uint32_t names_bytes, uint32_t tile_cap, uint32_t ragged_bytes = 0) {
   return 16 + tile_const_bytes(nf, names_bytes) + tile_cap + 64 + ragged_bytes;   // +64: template compares may look a few bytes past the tile
 }
@@ -286,6 +289,7 @@ __global__ void __launch_bounds__((PW + CW) * 32, (PW >= 12 ? TILE_MIN_CTAS : 8)
   uint32_t* rg_tile = rg_tot + ((A.n_cnt + 1u) & ~1u);                                // [0] tile id, [1] skip-copy flag, [2..14) look-back summaries of the warps
   // SequenceExample: per (column, row) element / byte counts of the FeatureLists, summed over the parse warps [n_var][32][2]
   uint32_t* sq_cnt = reinterpret_cast<uint32_t*>(tile_b + A.tile_cap + 64 + (RG ? tile_ragged_bytes((uint32_t)A.sch.n_var, A.n_cnt) : 0u));
+  uint8_t* sq_tab = reinterpret_cast<uint8_t*>(sq_cnt + (uint32_t)A.sch.n_var * 64u + 4u);      // [n_var][TILE_SQ_STEPS][32] elements per step (SEQ && RG)
   if (SEQ) for (uint32_t i = threadIdx.x; i < (uint32_t)A.sch.n_var * 64u; i += (PW + CW) * 32) sq_cnt[i] = 0u;
   // Tile id.  Ragged mode: tiles look back at their predecessors' totals, so ids are handed out in start order (a tile only
   // ever waits for tiles that are already running); otherwise the block index.
@@ -755,15 +759,26 @@ __global__ void __launch_bounds__((PW + CW) * 32, (PW >= 12 ? TILE_MIN_CTAS : 8)
         }
       }
       uint32_t steps = 0, tot_n = 0, tot_bytes = 0;
+      const uint32_t steps_start = p;
+      uint32_t my_step = wid;                                 // the next step this warp parses; the others it only hops over
       while (p < eend) {                                      // steps
         uint32_t flen;
+        if (steps != my_step) {
+          // not ours: `0A flen` -> one byte load + add (the step's owner checks the tag and the contents; an overshoot of the
+          // chain is caught by p != eend behind the loop)
+          const int32_t b1 = T.i8(p + 1);
+          if (b1 >= 0) p += 2u + (uint32_t)b1;
+          else { uint32_t q = p + 1; if (!t_len(T, q, eend, flen)) { bad = true; break; } p = q + flen; }
+          ++steps;
+          continue;
+        }
+        my_step += PW;
         if (T.u8(p) != 0x0A) { bad = true; break; }
         ++p;
         if (!t_len(T, p, eend, flen) || eend - p < flen) { bad = true; break; }
         const uint32_t fend = p + flen;
-        const bool mine = steps % PW == wid;                  // this warp parses the step; the others only hop over it
+        const uint32_t step_idx = steps, n_before = tot_n;
         ++steps;
-        if (!mine) { p = fend; continue; }
         if (flen == 0) { if (fd) bad = true; continue; }     // kind not set: an error if the schema wants the column
         uint32_t kt = T.u8(p++), llen;
         uint32_t kind = kt == 0x0A ? K_BYTES : kt == 0x12 ? K_FLOAT : kt == 0x1A ? K_INT64 : K_NONE;
@@ -801,16 +816,28 @@ __global__ void __launch_bounds__((PW + CW) * 32, (PW >= 12 ? TILE_MIN_CTAS : 8)
             if (bad || run) { bad = true; break; }
           }
         }
+        if (RG && fd && A.uniform_len[fd->var_slot] == TILE_RAGGED) {
+          // one-pass mode: the copy-out needs every step's element count (its place in the row = the sum of the steps before it)
+          const uint32_t cstep = tot_n - n_before;
+          if (step_idx >= TILE_SQ_STEPS || cstep > 255u) { bad = true; break; }
+          sq_tab[((uint32_t)fd->var_slot * TILE_SQ_STEPS + step_idx) * 32u + lane] = (uint8_t)cstep;
+        }
         p = fend;
       }
-      if (bad) break;
+      if (bad || p != eend) { bad = true; break; }
       if (fd) {
         if (tot_n) atomicAdd(&sq_cnt[(fd->var_slot * 32 + lane) * 2], tot_n);
         if (tot_bytes) atomicAdd(&sq_cnt[(fd->var_slot * 32 + lane) * 2 + 1], tot_bytes);
         if (owner) {
-          A.cnt[(size_t)fd->cnt_slot * A.n + row] = steps;
-          A.src[(size_t)fd->var_slot * A.n + row] = entry_pos + g0;
-          A.cflag[(size_t)fd->var_slot * A.n + row] = CF_FLIST;
+          if (RG && A.uniform_len[fd->var_slot] == TILE_RAGGED) {
+            if (steps > TILE_SQ_STEPS) { bad = true; break; }
+            rg_src[fd->var_slot * 32 + lane] = steps_start;              // where the steps begin; their number is the level-0 count
+            rg_cnt[fd->cnt_slot * 32 + lane] = steps;
+          } else {
+            A.cnt[(size_t)fd->cnt_slot * A.n + row] = steps;
+            A.src[(size_t)fd->var_slot * A.n + row] = entry_pos + g0;
+            A.cflag[(size_t)fd->var_slot * A.n + row] = CF_FLIST;
+          }
         }
       }
       p = eend;
@@ -828,6 +855,13 @@ __global__ void __launch_bounds__((PW + CW) * 32, (PW >= 12 ? TILE_MIN_CTAS : 8)
   asm volatile("bar.sync 1, %0;" ::"r"(PW * 32) : "memory");
   if (RG) {
     // ================= ragged columns, finished in this pass =================
+    if (SEQ) {                                                                    // FeatureList columns: the warps' summed element counts
+      for (uint32_t v = wid; v < (uint32_t)A.sch.n_var; v += PW) {
+        const DevField& fd = sfields[A.var_field[v]];
+        if (fd.depth == 2 && A.uniform_len[v] == TILE_RAGGED) rg_cnt[(fd.cnt_slot + 1) * 32 + lane] = sq_cnt[(v * 32 + lane) * 2];
+      }
+      asm volatile("bar.sync 1, %0;" ::"r"(PW * 32) : "memory");
+    }
     // (T) tile-local exclusive prefix of every count array over the 32 rows (lane = row); array a by warp a % W.  The tile's
     //     totals go out to the look-back table right away.
     const uint32_t nc = A.n_cnt, nc4 = (nc + 3u) & ~3u;                            // table rows are padded to whole uint4
@@ -917,9 +951,63 @@ __global__ void __launch_bounds__((PW + CW) * 32, (PW >= 12 ? TILE_MIN_CTAS : 8)
     asm volatile("bar.sync 1, %0;" ::"r"(PW * 32) : "memory");
     // (C) offsets + values: column v by warp v % W, lane = row.  Cells of consecutive rows are adjacent in the output.
     if (!rg_tile[1]) {
+      if (SEQ) {
+        // FeatureList columns (list<list<T>>, fixed-width T): EVERY warp walks the row's step chain again (one byte load per
+        // step) adding up the steps' element counts from the table the parse filled, and emits the steps s with s % W == its
+        // index: inner offset + values.  (One warp per column would leave the tile's other warps idle behind a 64-step walk.)
+        for (uint32_t v = 0; v < (uint32_t)A.sch.n_var; ++v) {
+          const DevField& fd = sfields[A.var_field[v]];
+          if (fd.depth != 2 || A.uniform_len[v] != TILE_RAGGED || !active) continue;
+          const uint32_t a0 = (uint32_t)fd.cnt_slot;
+          const uint32_t ex0 = rg_cnt[a0 * 32 + lane], ex1 = rg_cnt[(a0 + 1) * 32 + lane];
+          const uint32_t c0 = (lane == 31 ? rg_tot[a0] : rg_cnt[a0 * 32 + lane + 1]) - ex0;     // steps of this row
+          const uint32_t c1 = (lane == 31 ? rg_tot[a0 + 1] : rg_cnt[(a0 + 1) * 32 + lane + 1]) - ex1;   // elements of this row
+          const unsigned long long b0 = rg_base[a0], b1 = rg_base[a0 + 1];
+          int32_t* o1 = A.offs[v * 3 + 1];
+          if (wid == v % PW) {
+            int32_t* o0 = A.offs[v * 3];
+            o0[row] = (int32_t)(b0 + ex0);
+            if (row + 1 == n_rows) { o0[n_rows] = (int32_t)(b0 + ex0 + c0); o1[b0 + ex0 + c0] = (int32_t)(b1 + ex1 + c1); }
+          }
+          uint8_t* vals = reinterpret_cast<uint8_t*>(A.var_values[v]);
+          const uint8_t* tab = sq_tab + (size_t)v * TILE_SQ_STEPS * 32u + lane;
+          uint32_t q = rg_src[v * 32 + lane], run = 0, my_step = wid;
+          for (uint32_t st = 0; st < c0; ++st) {
+            uint32_t fl = T.u8(q + 1), hq = q + 2;                                   // `0A flen`
+            if (fl >= 0x80u) { hq = q + 1; t_len(T, hq, q + 6, fl); }
+            const uint32_t cn = tab[st * 32u];
+            if (st == my_step) {
+              my_step += PW;
+              const unsigned long long e0 = b1 + ex1 + run;
+              o1[b0 + ex0 + st] = (int32_t)e0;
+              if (cn) {
+                // Feature = kind llen 0A plen packed (validated canonical by the parse): skip the two headers
+                uint32_t x = hq + 1, l2;
+                t_len(T, x, hq + 6, l2);                                             // list length
+                ++x;                                                                 // 0A
+                t_len(T, x, x + 5, l2);                                              // packed length
+                if (fd.kind == K_FLOAT) {
+                  if (fd.elem_type == TFR_T_FLOAT32) { uint32_t* d = reinterpret_cast<uint32_t*>(vals) + e0; for (uint32_t i = 0; i < cn; ++i) d[i] = t_u32(T, x + 4 * i); }
+                  else { double* d = reinterpret_cast<double*>(vals) + e0; for (uint32_t i = 0; i < cn; ++i) d[i] = (double)__uint_as_float(t_u32(T, x + 4 * i)); }
+                } else {
+                  for (uint32_t i = 0; i < cn; ++i) {
+                    uint64_t y = 0; uint32_t sh = 0;
+                    for (;;) { const uint32_t b = T.u8(x++); y |= (uint64_t)(b & 0x7f) << sh; sh += 7; if (b < 0x80) break; }
+                    if (fd.elem_type == TFR_T_INT64) reinterpret_cast<int64_t*>(vals)[e0 + i] = (int64_t)y;
+                    else reinterpret_cast<int32_t*>(vals)[e0 + i] = (int32_t)(uint32_t)y;
+                  }
+                }
+              }
+            }
+            run += cn;
+            q = hq + fl;
+          }
+        }
+      }
       for (uint32_t v = wid; v < (uint32_t)A.sch.n_var; v += PW) {
         if (A.uniform_len[v] != TILE_RAGGED) continue;
         const DevField& fd = sfields[A.var_field[v]];
+        if (fd.depth == 2) continue;                           // (done above)
         const uint32_t a0 = (uint32_t)fd.cnt_slot;
         const uint32_t ex0 = rg_cnt[a0 * 32 + lane];
         const uint32_t c0 = (lane == 31 ? rg_tot[a0] : rg_cnt[a0 * 32 + lane + 1]) - ex0;       // this row's count at level 0
