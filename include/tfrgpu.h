@@ -162,7 +162,8 @@ int32_t tfr_decoder_get_profile(tfr_decoder*, double* ms /* [TFR_PROFILE_STAGES]
                                 int64_t* pass1_launches);
 /* counters since creation: [0] batches decoded, [1] submitted speculatively (no host sync), [2] of those redone after
  * the device raised a flag, [3] batches through count mode (ragged / learning), [4] through the general kernels,
- * [5] column shapes (re)learned                                                                                   */
+ * [5] column shapes (re)learned, [6] batches re-run by the single-pass kernel's transcoding instantiation (malformed
+ * UTF-8 in a string column)                                                                                       */
 int32_t tfr_decoder_get_stats(tfr_decoder*, int64_t* out, int32_t n /* <= 8 */);
 
 int32_t tfr_batch_wait(tfr_batch*);

@@ -286,7 +286,7 @@ class Decoder:
     def stats(self) -> dict:
         v = (C.c_int64 * 8)()
         _check(lib().tfr_decoder_get_stats(self.h, v, 8))
-        names = ["batches", "speculative_submits", "speculative_redone", "count_mode_batches", "general_path_batches", "shapes_learned"]
+        names = ["batches", "speculative_submits", "speculative_redone", "count_mode_batches", "general_path_batches", "shapes_learned", "transcode_reruns"]
         return {k: v[i] for i, k in enumerate(names)}
 
     def stream(self) -> int:

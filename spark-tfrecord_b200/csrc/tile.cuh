@@ -14,7 +14,7 @@
 // Mapping: one CTA = one tile = 32 consecutive records (rows 32t .. 32t+31, contiguous in memory),
 // TILE_PARSE_WARPS parse warps + TILE_CRC_WARPS CRC warps, all working on the same staged bytes.
 //   1. warp 0 arms an mbarrier; every lane issues cp.async.bulk (TMA bulk copy, SASS UBLKCP) of ITS record into its
-//      own slot of the tile (slot stride = an odd multiple of 16 bytes: the lanes' records spread over all eight
+//      place in the tile (records packed one behind the other at strides that are odd multiples of 16 bytes: they spread over all eight
 //      16-byte bank groups), and one more bulk copy brings the per-schema constants (5-bit CRC tables, zeroed merge
 //      words, field table, entry templates, names), which api.cu keeps in HBM in exactly the shared-memory layout.
 //   2. role split over the same staged bytes: the C CRC warps each fold a third of the 16-byte chunks of record
@@ -68,8 +68,9 @@ struct TileArgs {
   uint32_t n;                   // rows in the batch = stride of the scratch arrays; with n_dev: the CAPACITY the host sized everything for
   const uint32_t* n_dev;        // non-null: the number of rows is read here (FrameResult::n_records of this batch, still on the device when the
                                 // kernel is enqueued); more rows than `n` raise TF_OVERFLOW and nothing is decoded
-  uint32_t tile_cap;            // bytes of shared memory reserved for the record bytes of one tile (TILE_ROWS slots)
-  uint32_t slot;                // bytes per record slot: an ODD multiple of 16 (bank-group spread, see crc_chunks)
+  uint32_t tile_cap;            // bytes of shared memory reserved for the record bytes of one tile (32 records, packed)
+  uint32_t slot;                // != 0: fixed slots of this size (an ODD multiple of 16) per record; 0: records packed
+  uint32_t* tile_max;           // device word: max over the tiles of the packed bytes they would need (atomicMax), or null
   uint32_t verify;
   uint32_t names_bytes;
   DevSchema sch;
@@ -99,7 +100,7 @@ struct TileArgs {
   uint32_t* flags;              // [0] bit0: fall back to the general path, bit1: a uniform-shape speculation failed
 };
 
-enum { TF_FALLBACK = 1u, TF_SHAPE = 2u, TF_OVERFLOW = 4u };
+enum { TF_FALLBACK = 1u, TF_SHAPE = 2u, TF_OVERFLOW = 4u, TF_XCODE = 8u };
 #define TILE_RAGGED (-2)
 
 // ---- mbarrier + bulk async copy (PTX; sm_90+) ---------------------------------------------------
@@ -209,6 +210,13 @@ __device__ __forceinline__ void t_copy_out(const Tile& t, uint32_t src, uint8_t*
   for (; i < l; ++i) dst[i] = (uint8_t)t.u8(src + i);
 }
 
+// a string cell of a row that holds malformed UTF-8 somewhere (rare): kept out of line so that the copy-out stays small.
+// Well-formed (or pure ASCII) bytes are copied, anything else is re-encoded the way Java does; returns the bytes written.
+__device__ __noinline__ uint32_t t_xcode_cell(const uint8_t* src, uint32_t raw, uint8_t* dst) {      // dst == nullptr: length only
+  if (all_ascii(src, raw) || utf8_valid(src, raw)) { if (dst) for (uint32_t i = 0; i < raw; ++i) dst[i] = src[i]; return raw; }
+  return java_utf8_transcode(src, raw, dst);
+}
+
 // ---- per-thread CRC-32C over shared memory: 8 bytes per step through 13 conflict-free 5-bit tables (CrcTables::g5) ----
 __device__ __forceinline__ uint32_t crc_fold8(const uint32_t* g, uint32_t c, uint32_t lo, uint32_t hi) {
   const uint32_t a = lo ^ c;
@@ -265,7 +273,10 @@ __host__ __device__ inline uint32_t tile_smem_bytes(uint32_t nf, uint32_t names_
 // (45 resident warps).  Small records: a tile is a few KB, eight fit an SM, and 4 + 1 warps per tile give the same number of
 // resident warps with three times as many records in flight (a tile's life is a latency chain: offsets -> bulk copy -> parse
 // -> barriers -> stores) and a third of the hops (every parse warp walks every entry).
-template <bool SEQ, bool RG, int PW, int CW>
+// XC: the kernel can re-encode malformed UTF-8 strings of ragged columns itself (calls into the out-of-line Java transcoder).
+// Merely containing those calls costs the kernel 7 % (474 vs 510 GB/s on ragged configs[1], never executing them), so the
+// default instantiation has none: it raises TF_XCODE instead and the host re-runs the batch -- and the next ones -- with XC.
+template <bool SEQ, bool RG, int PW, int CW, bool XC>
 __global__ void __launch_bounds__((PW + CW) * 32, (PW >= 12 ? TILE_MIN_CTAS : 8)) decode_tile_kernel(TileArgs A) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
@@ -279,7 +290,7 @@ __global__ void __launch_bounds__((PW + CW) * 32, (PW >= 12 ? TILE_MIN_CTAS : 8)
   uint8_t* tile_b = sbase + tile_schema_smem(nf, A.names_bytes);
   const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;                          // warps 0..W-1 parse, warp W = CRC
 
-  // Record r of the tile is copied into its own slot: bytes [off_r & ~15, off_r + framed length) -> tile + r * slot.
+  // Record r of the tile is copied to its place in the tile: bytes [off_r & ~15, off_r + framed length) -> tile + rbase_r.
   // (cp.async.bulk wants 16-byte aligned source, destination and size; the record starts (off_r & 15) bytes into its slot.)
   // ragged scratch behind the tile bytes (see tile_ragged_bytes)
   uint32_t* rg_src = reinterpret_cast<uint32_t*>(tile_b + A.tile_cap + 64);           // [n_var][32] tile offset of each cell's bytes
@@ -329,7 +340,24 @@ __global__ void __launch_bounds__((PW + CW) * 32, (PW >= 12 ? TILE_MIN_CTAS : 8)
   if (active && b_lo < mis) b_lo += 16u;
   if (active && b_hi > lim) b_hi = lim & ~15u;
   const uint32_t bulk_bytes = (active && b_hi > b_lo) ? b_hi - b_lo : 0u;
-  if (__any_sync(FULLMASK, cbytes + 32u > A.slot)) {                       // a record too large for its slot: general path
+  // Where the records sit in the tile.  A record's stride = its 16-byte groups + 32 bytes of slack (word loads of the parse
+  // look a little past a record), made an ODD number of 16-byte units.
+  //   fixed slots (A.slot != 0): every record at lane * slot, slot = the largest record's stride.  The 32 lanes then start in
+  //     all eight 16-byte bank groups, four lanes each: the minimum of shared-memory wavefronts for the 16-byte CRC loads and
+  //     the parse's word loads (same-sized records at an even stride put every lane on the same banks).
+  //   packed (A.slot == 0): one behind the other at their own strides.  Records of very different sizes do not each pay for the
+  //     largest one -- the tile is sized for a typical SUM of 32 records.  The host picks this when it lets one more tile
+  //     live on an SM.
+  uint32_t stride = active ? (cbytes + 32u + 15u) & ~15u : 0u;
+  if (active && ((stride >> 4) & 1u) == 0u) stride += 16u;
+  // packed: every stride is padded to 16 bytes more than a multiple of 128, so that record r starts in bank group r % 8 like
+  // with fixed odd slots (64 bytes of padding per record on average; a plain prefix sum gives the places)
+  uint32_t tile_tot;
+  uint32_t rbase = warp_excl_scan_u32(active ? ((stride + 111u) & ~127u) + 16u : 0u, tile_tot);
+  uint32_t tile_need = tile_tot;                                           // bytes of the tile this layout takes
+  if (A.slot) { rbase = lane * A.slot; tile_need = __any_sync(FULLMASK, stride > A.slot) ? 0xffffffffu : 0u; }
+  if (threadIdx.x == 0 && A.tile_max) atomicMax(A.tile_max, tile_tot);     // (the packed size, whatever the layout: what the next batch's tiles are sized from)
+  if (tile_need > A.tile_cap) {                                             // the tile's records do not fit: general path
     if (threadIdx.x == 0) {
       atomicOr(A.flags, TF_FALLBACK);
       if (RG) {                                                            // successors must not wait for this tile (the batch is redone anyway)
@@ -351,9 +379,9 @@ __global__ void __launch_bounds__((PW + CW) * 32, (PW >= 12 ? TILE_MIN_CTAS : 8)
       bulk_g2s(smem_raw + 16, A.consts, A.const_bytes, bar);      // CRC tables, zeroed seen words, schema, templates, names
     }
     __syncwarp();
-    if (bulk_bytes) bulk_g2s(tile_b + lane * A.slot + (b_lo - g_lo), base + b_lo, bulk_bytes, bar);
+    if (bulk_bytes) bulk_g2s(tile_b + rbase + (b_lo - g_lo), base + b_lo, bulk_bytes, bar);
     if (active) {
-      uint8_t* sl = tile_b + lane * A.slot;
+      uint8_t* sl = tile_b + rbase;
       const uint32_t e1 = min(b_lo, lim);
       if (b_lo > g_lo) for (uint32_t i = mis; i < e1; ++i) sl[i - g_lo] = base[i];                                  // clipped first group
       if (b_hi < g_lo + cbytes) for (uint32_t i = max(b_hi, e1); i < lim; ++i) sl[i - g_lo] = base[i];             // clipped last group
@@ -363,9 +391,9 @@ __global__ void __launch_bounds__((PW + CW) * 32, (PW >= 12 ? TILE_MIN_CTAS : 8)
   mbar_wait(bar, 0);
 
   const uint32_t len = flen - 16;
-  const uint32_t pay = lane * A.slot + head + 12;                 // payload offset inside the tile
+  const uint32_t pay = rbase + head + 12;                         // payload offset inside the tile
   const uint32_t end = pay + len;
-  const uint32_t g0 = (off - head) - lane * A.slot;               // tile offset + g0 = offset in the batch (mod 2^32)
+  const uint32_t g0 = (off - head) - rbase;                       // tile offset + g0 = offset in the batch (mod 2^32)
   Tile T;
   T.b = tile_b;
   asm volatile("mov.u32 %0, %1;" : "=r"(T.s) : "r"(smem_u32(tile_b)) : "memory");   // ordered after mbar_wait
@@ -551,20 +579,22 @@ __global__ void __launch_bounds__((PW + CW) * 32, (PW >= 12 ? TILE_MIN_CTAS : 8)
           ++p;
           const uint32_t lp = p;
           if (!t_len(T, p, eend, bl) || eend - p < bl) { bad = true; break; }
-          uint32_t ol = bl;                                                   // bytes this element contributes to the column
           if (is_str) {
             // StringType = Java UTF-8 decode/re-encode: identity for well-formed input.  Malformed input becomes U+FFFD per
-            // malformed unit (java_utf8_transcode): a ragged column takes the re-encoded length here and the copy-out
-            // transcodes; a uniform or count-mode column leaves the row to the general path.
+            // malformed unit (java_utf8_transcode): a ragged column flags the cell, its length is corrected behind the parse
+            // barrier and the copy-out re-encodes; a uniform or count-mode column leaves the row to the general path.
             uint32_t acc = 0;
             for (uint32_t i = 0; i < bl; ++i) acc |= T.u8(p + i);
             if (acc >= 0x80 && !utf8_valid(T.b + p, bl)) {
-              if (RG && A.uniform_len[fd->var_slot] == TILE_RAGGED) { ol = java_utf8_transcode(T.b + p, bl, nullptr); xcode = true; }
-              else { bad = true; break; }
+              if (RG && XC && A.uniform_len[fd->var_slot] == TILE_RAGGED) xcode = true;      // counted with its raw length here, fixed up behind the parse barrier
+              else {
+                if (RG && A.uniform_len[fd->var_slot] == TILE_RAGGED) atomicOr(A.flags, TF_XCODE);   // the XC instantiation can take this batch
+                bad = true; break;
+              }
             }
           }
-          if (n == 0) { first_off = lp + g0; first_len = ol; first_data = p; }
-          ++n; total += ol;
+          if (n == 0) { first_off = lp + g0; first_len = bl; first_data = p; }
+          ++n; total += bl;
           p += bl;
         }
         if (bad) break;
@@ -576,6 +606,7 @@ __global__ void __launch_bounds__((PW + CW) * 32, (PW >= 12 ? TILE_MIN_CTAS : 8)
               // (a malformed string: the copy-out re-reads the raw length from the varint in front of the data)
               rg_src[fd->var_slot * 32 + lane] = first_data | (xcode ? 0x80000000u : 0u);
               rg_cnt[fd->cnt_slot * 32 + lane] = first_len;
+              if (xcode) atomicOr(&sseen[161], 1u);
             } else if (ul >= 0) {
               if ((uint32_t)ul != first_len) shape_bad = 1;
               else {
@@ -596,6 +627,7 @@ __global__ void __launch_bounds__((PW + CW) * 32, (PW >= 12 ? TILE_MIN_CTAS : 8)
           } else {
             // ArrayType(String/Binary): two offset levels -> ragged or count mode (never uniform)
             if (RG && A.uniform_len[fd->var_slot] == TILE_RAGGED) {
+              if (xcode) atomicOr(&sseen[161], 1u);
               rg_src[fd->var_slot * 32 + lane] = body | (xcode ? 0x80000000u : 0u);
               rg_cnt[fd->cnt_slot * 32 + lane] = n;
               rg_cnt[(fd->cnt_slot + 1) * 32 + lane] = total;
@@ -855,6 +887,30 @@ __global__ void __launch_bounds__((PW + CW) * 32, (PW >= 12 ? TILE_MIN_CTAS : 8)
   asm volatile("bar.sync 1, %0;" ::"r"(PW * 32) : "memory");
   if (RG) {
     // ================= ragged columns, finished in this pass =================
+    if (XC && sseen[161]) {
+      // Some string cell of this tile holds malformed UTF-8 (rare): its bytes in the column are the Java re-encoding, whose
+      // length replaces the raw one before the offsets are computed.  Kept out of the parse loop (calls there cost the hot
+      // path registers).
+      for (uint32_t v = wid; v < (uint32_t)A.sch.n_var; v += PW) {
+        const DevField& fd = sfields[A.var_field[v]];
+        // (the source word of an absent or empty cell was never written: the count decides first)
+        if (A.uniform_len[v] != TILE_RAGGED || fd.elem_type != TFR_T_STRING || !active || rg_cnt[fd.cnt_slot * 32 + lane] == 0u || !(rg_src[v * 32 + lane] >> 31)) continue;
+        const uint32_t src = rg_src[v * 32 + lane] & 0x7fffffffu;
+        if (fd.depth == 0) {
+          uint32_t k = 1;
+          while (k < 5 && (T.u8(src - 1 - k) & 0x80u)) ++k;                       // the raw length: the varint in front of the data
+          uint32_t q = src - k, raw = 0;
+          t_len(T, q, src, raw);
+          rg_cnt[fd.cnt_slot * 32 + lane] = t_xcode_cell(T.b + src, raw, nullptr);
+        } else if (fd.depth == 1) {
+          const uint32_t cnt = rg_cnt[fd.cnt_slot * 32 + lane];
+          uint32_t q = src, tot = 0;
+          for (uint32_t i = 0; i < cnt; ++i) { uint32_t bl = 0; ++q; t_len(T, q, q + 5, bl); tot += t_xcode_cell(T.b + q, bl, nullptr); q += bl; }
+          rg_cnt[(fd.cnt_slot + 1) * 32 + lane] = tot;
+        }
+      }
+      asm volatile("bar.sync 1, %0;" ::"r"(PW * 32) : "memory");
+    }
     if (SEQ) {                                                                    // FeatureList columns: the warps' summed element counts
       for (uint32_t v = wid; v < (uint32_t)A.sch.n_var; v += PW) {
         const DevField& fd = sfields[A.var_field[v]];
@@ -1022,14 +1078,14 @@ __global__ void __launch_bounds__((PW + CW) * 32, (PW >= 12 ? TILE_MIN_CTAS : 8)
         const bool xcode = rg_src[v * 32 + lane] >> 31;          // a malformed UTF-8 string in this cell: re-encode instead of copy
         uint8_t* vals = reinterpret_cast<uint8_t*>(A.var_values[v]);
         if (fd.depth == 0) {                                   // scalar string / binary: c0 bytes
-          if (xcode) {
+          if (XC && xcode) {
             // raw length: the varint that ends right in front of the data (its last byte has the top bit clear, the ones before
             // it set; the tag 0A in front of it has it clear again)
             uint32_t k = 1;
             while (k < 5 && (T.u8(src - 1 - k) & 0x80u)) ++k;
             uint32_t q = src - k, raw = 0;
             t_len(T, q, src, raw);
-            java_utf8_transcode(T.b + src, raw, vals + b0 + ex0);
+            if (XC) t_xcode_cell(T.b + src, raw, vals + b0 + ex0);
           }
           else t_copy_out(T, src, vals + b0 + ex0, c0);
         } else if (fd.kind == K_FLOAT) {                       // packed floats
@@ -1054,7 +1110,7 @@ __global__ void __launch_bounds__((PW + CW) * 32, (PW >= 12 ? TILE_MIN_CTAS : 8)
             t_len(T, qq, q + 5, bl);
             q = qq;
             o1[b0 + ex0 + i] = (int32_t)vpos;
-            if (xcode && !all_ascii(T.b + q, bl) && !utf8_valid(T.b + q, bl)) vpos += java_utf8_transcode(T.b + q, bl, vals + vpos);
+            if (XC && xcode) vpos += t_xcode_cell(T.b + q, bl, vals + vpos);
             else { t_copy_out(T, q, vals + vpos, bl); vpos += bl; }
             q += bl;
           }

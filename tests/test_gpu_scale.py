@@ -459,6 +459,11 @@ def test_malformed_utf8_in_ragged_string_columns_is_not_a_cliff(native, oracle):
         s0 = dec.stats()
         b = dec.submit(dirty); _check_batch(oracle, b, dirty, sch, what="malformed UTF-8 in ragged string columns"); b.release()
         s1 = dec.stats()
-        assert s1["speculative_submits"] == s0["speculative_submits"] + 1 and s1["speculative_redone"] == s0["speculative_redone"], (s0, s1)
+        # the default kernel met the first malformed string and handed the batch to its transcoding instantiation: one more
+        # single-pass run, not the general path
+        assert s1["transcode_reruns"] == 1 and s1["speculative_redone"] == s0["speculative_redone"] and s1["general_path_batches"] == 0, (s0, s1)
+        b = dec.submit(dirty); _check_batch(oracle, b, dirty, sch, what="malformed UTF-8, transcoding kernel already active"); b.release()
+        s2 = dec.stats()
+        assert s2["transcode_reruns"] == 1 and s2["speculative_submits"] == s1["speculative_submits"] + 1 and s2["speculative_redone"] == s1["speculative_redone"], (s1, s2)
     finally:
         dec.close()
