@@ -758,21 +758,25 @@ def run_ours(args):
     # ---------------- end to end: pinned host -> device -> pinned host, one handle, one thread ----------------
     e2e = None
     if not args.no_e2e:
-        d2 = _native.Decoder(schema, 0, dev)
-        S = d2.num_staging_slots()
-        stages = []
-        for s in range(S):
-            src = h_batches[s % len(h_batches)]
-            st = d2.staging_slot(s, src.nbytes)
-            st[: src.nbytes] = src            # the JVM side writes file bytes here; not part of the timed region
-            stages.append((st, src.nbytes))
-        for i in range(3):
-            b, used = d2.decode(stages[0][0], nbytes=stages[0][1])
-            b.to_host_raw()
-            b.release()
         d2h = [0]
 
-        def e2e_batches(count):
+        def e2e_setup():
+            d2 = _native.Decoder(schema, 0, dev)
+            S = d2.num_staging_slots()
+            stages = []
+            for s in range(S):
+                src = h_batches[s % len(h_batches)]
+                st = d2.staging_slot(s, src.nbytes)
+                st[: src.nbytes] = src            # the JVM side writes file bytes here; not part of the timed region
+                stages.append((st, src.nbytes))
+            for i in range(3):
+                b, used = d2.decode(stages[0][0], nbytes=stages[0][1])
+                b.to_host_raw()
+                b.release()
+            return d2, stages
+
+        def e2e_batches(d2, stages, count, out):
+            S = len(stages)
             inflight = [None] * S
             tot = 0
             for i in range(count):
@@ -792,30 +796,52 @@ def run_ours(args):
                     ob.to_host_raw()
                     assert ob.info["error_code"] == 0
                     ob.release()
-            return tot
+            out.append(tot)
 
-        e2e_batches(max(2 * S, args.warmup))
-        barrier()
-        t0 = time.perf_counter()
-        e2e_bytes = e2e_batches(args.steps * args.e2e_batches_per_step)
-        torch.cuda.synchronize()
-        barrier()
-        t_e2e = time.perf_counter() - t0
-        e2e = (e2e_bytes, t_e2e, d2h[0], d2.stats())
-        d2.close()
+        def e2e_run(handles, count):
+            """`count` batches over len(handles) decoder handles, one host thread each"""
+            outs, ths = [], []
+            per = [count // len(handles) + (1 if k < count % len(handles) else 0) for k in range(len(handles))]
+            for (d2, stages), c in zip(handles, per):
+                ths.append(threading.Thread(target=e2e_batches, args=(d2, stages, c, outs)))
+            for t in ths:
+                t.start()
+            for t in ths:
+                t.join()
+            return sum(outs)
+
+        variants = {}
+        handles = [e2e_setup()]
+        for n_handles in (1, 2):
+            while len(handles) < n_handles:
+                handles.append(e2e_setup())
+            e2e_run(handles[:n_handles], max(2 * 3 * n_handles, args.warmup))
+            barrier()
+            t0 = time.perf_counter()
+            nbytes_e2e = e2e_run(handles[:n_handles], args.steps * args.e2e_batches_per_step)
+            torch.cuda.synchronize()
+            barrier()
+            variants[n_handles] = (nbytes_e2e, time.perf_counter() - t0)
+        e2e_stats = handles[0][0].stats()
+        for d2, _ in handles:
+            d2.close()
+        e2e = (variants, d2h[0], e2e_stats)
 
     clk = clocks.stop()
 
     # ---------------- reduce over ranks ----------------
     if use_dist:
-        t = torch.tensor([ms, t_wall, e2e[1] if e2e else 0.0, cfg5[1] if cfg5 else 0.0], dtype=torch.float64, device=f"cuda:{dev}")
+        ev = e2e[0] if e2e else {1: (0, 0.0), 2: (0, 0.0)}
+        t = torch.tensor([ms, t_wall, ev[1][1], ev[2][1], cfg5[1] if cfg5 else 0.0], dtype=torch.float64, device=f"cuda:{dev}")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        s = torch.tensor([float(in_bytes), float(e2e[0] if e2e else 0), float(cfg5[0] if cfg5 else 0), float(cfg5[3] if cfg5 else 0)], dtype=torch.float64, device=f"cuda:{dev}")
+        s = torch.tensor([float(in_bytes), float(ev[1][0]), float(ev[2][0]), float(cfg5[0] if cfg5 else 0), float(cfg5[3] if cfg5 else 0)], dtype=torch.float64, device=f"cuda:{dev}")
         dist.all_reduce(s, op=dist.ReduceOp.SUM)
-        ms, t_wall, t_e2e_max, cfg5_ms_max = t.tolist()
-        tot_in, tot_e2e, cfg5_bytes, cfg5_blocks = s.tolist()
+        ms, t_wall, t_e2e_1, t_e2e_2, cfg5_ms_max = t.tolist()
+        tot_in, tot_e2e_1, tot_e2e_2, cfg5_bytes, cfg5_blocks = s.tolist()
     else:
-        tot_in, tot_e2e, t_e2e_max = float(in_bytes), float(e2e[0] if e2e else 0), (e2e[1] if e2e else 0.0)
+        ev = e2e[0] if e2e else {1: (0, 0.0), 2: (0, 0.0)}
+        tot_in = float(in_bytes)
+        tot_e2e_1, t_e2e_1, tot_e2e_2, t_e2e_2 = float(ev[1][0]), ev[1][1], float(ev[2][0]), ev[2][1]
         cfg5_ms_max, cfg5_bytes, cfg5_blocks = (cfg5[1], float(cfg5[0]), float(cfg5[3])) if cfg5 else (0.0, 0.0, 0.0)
 
     if rank != 0:
@@ -887,11 +913,17 @@ def run_ours(args):
                     "does not overlap the decode of block t as it does in the headline loop"}
     if e2e:
         eb = args.e2e_batches_per_step
-        line["e2e"] = {"value": tot_e2e / t_e2e_max / 1e9, "unit": UNIT, "h2d_bytes_per_step": int(batch_bytes[0]) * eb,
-                       "d2h_bytes_per_step": int(e2e[2]) * eb, "batches_per_step": eb, "steps": args.steps,
-                       "pipeline": "ONE decoder handle on ONE thread: tfr_decode_submit (H2D on the copy stream, frame index, tile kernel) + "
-                                   "tfr_batch_to_host_async (D2H on the copy-out stream), 3 pinned staging slots in, pinned Arrow buffers out",
-                       "stats": e2e[3]}
+        v1 = tot_e2e_1 / t_e2e_1 / 1e9 if t_e2e_1 > 0 else 0.0
+        v2 = tot_e2e_2 / t_e2e_2 / 1e9 if t_e2e_2 > 0 else 0.0
+        line["e2e"] = {"value": max(v1, v2), "unit": UNIT, "h2d_bytes_per_step": int(batch_bytes[0]) * eb,
+                       "d2h_bytes_per_step": int(e2e[1]) * eb, "batches_per_step": eb, "steps": args.steps,
+                       "one_handle_one_thread": v1, "two_handles_two_threads": v2,
+                       "pipeline": "per decoder handle ONE host thread: tfr_decode_submit (H2D on the copy stream, frame index, tile kernel, no host sync) + "
+                                   "tfr_batch_to_host_async (D2H on the copy-out stream), 3 pinned staging slots in, pinned Arrow buffers out; value = the better of one "
+                                   "handle / one thread and two handles / two threads (what two Spark tasks sharing a GPU do)",
+                       "ceiling": "tools/pcie_probe.py on this pool (profiles/r2_pcie_probe_*.json): plain pinned copies of the same sizes in both directions at once move "
+                                  "51.7 + 35.1 GB/s on one GPU, 227 + 154 GB/s on eight",
+                       "stats": e2e[2]}
     # ---------------- CPU baseline beside it (rank 0, N=1 only) ----------------
     if not args.no_cpu and world == 1:
         cores = host_cores()
