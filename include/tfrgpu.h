@@ -155,6 +155,7 @@ int32_t tfr_decoder_stream(tfr_decoder*, void** cuda_stream /* cudaStream_t */);
  *   ms[0] frame index (scan+check+repair+finish+emit)   ms[1] decode pass 1 (CRC + parse)
  *   ms[2] scans + summary                               ms[3] decode pass 2 (variable-width emit)
  *   ms[4] validity pack                                 ms[5] H2D of the input (host input only)
+ *   ms[6] D2H of the Arrow buffers (tfr_batch_to_host[_async])
  * plus the number of kernel launches and of pass-1 launches.                                  */
 #define TFR_PROFILE_STAGES 8
 int32_t tfr_decoder_set_profiling(tfr_decoder*, int32_t enable);

@@ -302,7 +302,7 @@ class Decoder:
         nl = C.c_int64()
         n1 = C.c_int64()
         _check(lib().tfr_decoder_get_profile(self.h, ms, C.byref(nl), C.byref(n1)))
-        names = ["frame_index", "pass1", "scan", "pass2", "pack_validity", "h2d"]
+        names = ["frame_index", "pass1", "scan", "pass2", "pack_validity", "h2d", "d2h"]
         return {"ms": {k: ms[i] for i, k in enumerate(names)}, "launches": nl.value, "pass1_launches": n1.value}
 
     def decode(self, data, is_final: bool = True, nbytes: Optional[int] = None):

@@ -19,6 +19,7 @@
 #include "decode.cuh"
 #include "encode.cuh"
 #include "encode_tile.cuh"
+#include "bytes_tile.cuh"
 #include "frame.cuh"
 #include "host_util.h"
 #include "infer.cuh"

@@ -467,3 +467,137 @@ def test_malformed_utf8_in_ragged_string_columns_is_not_a_cliff(native, oracle):
         assert s2["transcode_reruns"] == 1 and s2["speculative_submits"] == s1["speculative_submits"] + 1 and s2["speculative_redone"] == s1["speculative_redone"], (s1, s2)
     finally:
         dec.close()
+
+
+def _frame_payloads(payloads):
+    from oracle import pyref
+    return np.frombuffer(b"".join(pyref.frame_fast(p) for p in payloads), dtype=np.uint8)
+
+
+def _bytes_rows_of(batch):
+    c = batch.to_host()[0]
+    o = c.offsets[0]
+    v = c.values.view(np.uint8)
+    return c, [v[o[i]:o[i + 1]].tobytes() for i in range(len(o) - 1)]
+
+
+def test_bytearray_rows_single_pass_and_pipelined(native, oracle):
+    """recordType=ByteArray through decode_bytes_kernel: the synchronising decode, the pipelined submit (device buffers at every
+    alignment, host staging), a CRC error and a record larger than the slot in the middle of the pipeline -- rows, offsets,
+    validity and the error position must be the oracle's (M/TFRecordDeserializer.scala:17-19)"""
+    import torch
+    rng = np.random.default_rng(2024)
+    sch = byte_array_schema()
+
+    def make(n, lo, hi, seed):
+        r = np.random.default_rng(seed)
+        sizes = r.integers(lo, hi, n)
+        sizes[:: 97] = 0                                            # empty payloads are rows too
+        blob = r.integers(0, 256, int(sizes.sum()), dtype=np.uint8).tobytes()
+        pos = np.concatenate([[0], np.cumsum(sizes)])
+        return [blob[pos[i]:pos[i + 1]] for i in range(n)]
+
+    batches = [make(n, lo, hi, 50 + i) for i, (n, lo, hi) in enumerate([(30000, 0, 2000), (30011, 0, 2000), (29000, 0, 2040), (31000, 0, 1990), (30000, 900, 1100), (1, 5, 6)])]
+    datas = [_frame_payloads(p) for p in batches]
+    dec = native.Decoder(sch, TFR_RT_BYTE_ARRAY)
+    try:
+        # synchronising decode
+        b, used = dec.decode(torch.from_numpy(datas[0].copy()).cuda())
+        assert used == len(datas[0]) and b.info["error_code"] == 0 and b.n_rows == len(batches[0]), b.info
+        c, rows = _bytes_rows_of(b)
+        assert rows == batches[0] and c.null_count == 0 and np.all(np.unpackbits(c.validity, bitorder="little")[: b.n_rows] == 1)
+        want = oracle.decode(datas[0], sch, 2)
+        assert_columns_equal(b.to_host(), want.columns, ["byteArray"], "ByteArray rows, first decode")
+        b.release()
+        assert dec.stats()["general_path_batches"] == 0, dec.stats()
+        # pipelined, device buffers starting at every alignment mod 16
+        inflight = []
+        keep = []
+        for i in range(1, len(datas)):
+            t = torch.empty(len(datas[i]) + 16, dtype=torch.uint8, device="cuda")
+            view = t[i % 16: i % 16 + len(datas[i])]
+            view.copy_(torch.from_numpy(datas[i].copy()))
+            keep.append(t)
+            inflight.append((i, dec.submit(view)))
+        for i, b in inflight:
+            assert b.info["error_code"] == 0 and b.info["consumed_bytes"] == len(datas[i]) and b.n_rows == len(batches[i]), (i, b.info)
+            assert _bytes_rows_of(b)[1] == batches[i], f"pipelined ByteArray batch {i}"
+            b.release()
+        st = dec.stats()
+        assert st["speculative_submits"] >= len(datas) - 2 and st["general_path_batches"] == 0, st
+        # host input through the staging slots + asynchronous copy-out
+        inflight = []
+        for i in range(1, 5):
+            slot = i % dec.num_staging_slots()
+            for j, b in [x for x in inflight if x[0] % dec.num_staging_slots() == slot]:
+                assert _bytes_rows_of(b)[1] == batches[j]
+                b.release(); inflight.remove((j, b))
+            sb = dec.staging_slot(slot, len(datas[i]))
+            sb[: len(datas[i])] = datas[i]
+            b = dec.submit(sb, nbytes=len(datas[i]))
+            b.to_host_async()
+            inflight.append((i, b))
+        for j, b in inflight:
+            assert _bytes_rows_of(b)[1] == batches[j], f"staged ByteArray batch {j}"
+            b.release()
+        # a flipped payload bit in the middle of a pipelined batch: the error is reported at that record, rows before it stand
+        k = 12345
+        offs = record_offsets(datas[1])
+        bad = datas[1].copy(); bad[offs[k] + 12 + len(batches[1][k]) // 2] ^= 4
+        if len(batches[1][k]) == 0:
+            bad[offs[k] + 12] ^= 4               # (the CRC field itself)
+        b = dec.submit(torch.from_numpy(bad).cuda())
+        assert b.info["error_code"] == A.TFR_E_CRC_DATA and b.info["error_row"] == k and b.n_rows == k, b.info
+        assert _bytes_rows_of(b)[1] == batches[1][:k]
+        b.release()
+        # a flipped length-CRC bit
+        bad = datas[2].copy(); offs2 = record_offsets(datas[2]); bad[offs2[777] + 9] ^= 1
+        b = dec.submit(torch.from_numpy(bad).cuda())
+        assert b.info["error_code"] == A.TFR_E_CRC_LENGTH and b.info["error_row"] == 777 and b.n_rows == 777, b.info
+        b.release()
+        # a record much larger than anything seen so far (slot overflow -> redone), then one too large for any tile (general kernels)
+        for big in (5000, 300000):
+            rows = list(batches[3][:5000]); rows[2500] = rng.integers(0, 256, big, dtype=np.uint8).tobytes()
+            d = _frame_payloads(rows)
+            b = dec.submit(torch.from_numpy(d.copy()).cuda())
+            assert b.info["error_code"] == 0 and b.n_rows == len(rows), b.info
+            assert _bytes_rows_of(b)[1] == rows, f"ByteArray batch with a {big}-byte record"
+            b.release()
+        # and back to the pipeline afterwards
+        b = dec.submit(torch.from_numpy(datas[4].copy()).cuda())
+        assert _bytes_rows_of(b)[1] == batches[4]
+        b.release()
+    finally:
+        dec.close()
+
+
+def test_bytearray_exact_end_buffer(native, oracle):
+    """ByteArray rows from a device allocation that ends exactly at data + nbytes (no padding, see the Example variant above)"""
+    import torch
+    torch.cuda.init()
+    rt = ctypes.CDLL("libcudart.so.12")
+    rt.cudaMalloc.argtypes = [ctypes.POINTER(ctypes.c_void_p), ctypes.c_size_t]
+    rt.cudaMemcpy.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int]
+    rt.cudaFree.argtypes = [ctypes.c_void_p]
+    rng = np.random.default_rng(5)
+    sch = byte_array_schema()
+    dec = native.Decoder(sch, TFR_RT_BYTE_ARRAY)
+    ptrs = []
+    try:
+        for n_rec, last in ((4000, 1001), (4001, 7), (33, 1), (1, 3), (2, 0)):
+            rows = [rng.integers(0, 256, int(s), dtype=np.uint8).tobytes() for s in list(rng.integers(0, 1500, n_rec - 1)) + [last]]
+            data = _frame_payloads(rows)
+            nb = len(data)
+            p = ctypes.c_void_p()
+            assert rt.cudaMalloc(ctypes.byref(p), nb) == 0
+            ptrs.append(p)
+            assert rt.cudaMemcpy(p, data.ctypes.data, nb, 1) == 0
+            for it in range(2):
+                b, used = dec.decode((p.value, nb, 1))
+                assert used == nb and b.info["error_code"] == 0 and b.n_rows == n_rec, b.info
+                assert _bytes_rows_of(b)[1] == rows, f"exact-end ByteArray buffer, {n_rec} records, decode #{it + 1}"
+                b.release()
+    finally:
+        dec.close()
+        for p in ptrs:
+            rt.cudaFree(p)
