@@ -6,9 +6,10 @@
 //
 // Same tile machinery as decode_tile_kernel (tile.cuh): CTA = 32 consecutive records, lane = record, each record bulk-copied
 // (cp.async.bulk + mbarrier) into its own shared-memory slot at an odd multiple of 16 bytes, so the 32 lanes' 16-byte CRC
-// loads spread over all bank groups.  All NW warps first share the CRC of the 32 payloads (each folds a range of every
-// record's 16-byte chunks, ranges are joined with one GF(2) multiply), then copy the payloads out, one record per warp at
-// a time, 4 bytes per lane (conflict-free in shared memory, 128-byte coalesced in global memory).
+// loads spread over all bank groups.  CW warps share the CRC of the 32 payloads (each folds a range of every record's
+// 16-byte chunks, ranges are joined with one GF(2) multiply -- 190 instructions, so ranges are kept long: CW is 2 when many
+// tiles fit an SM and grows only when large records leave room for few); XW warps meanwhile copy the payloads out, one
+// record per warp at a time, 4 bytes per lane (conflict-free in shared memory, 128-byte coalesced in global memory).
 #pragma once
 #include "tile.cuh"
 
@@ -17,8 +18,8 @@ __host__ __device__ inline uint32_t bytes_smem_bytes(uint32_t tile_cap) { return
 
 // TileArgs fields used: data, nbytes, misalign, rec_off, n, n_dev, tile_cap, slot (never 0), tile_max, verify, consts,
 // bitmaps (validity of the one column), offs[0] (Arrow offsets), var_values[0] (the bytes), totals (nullable), cap (nullable), flags
-template <int NW>
-__global__ void __launch_bounds__(NW * 32, 4) decode_bytes_kernel(TileArgs A) {
+template <int CW, int XW>
+__global__ void __launch_bounds__((CW + XW) * 32) decode_bytes_kernel(TileArgs A) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
   uint32_t* s8 = reinterpret_cast<uint32_t*>(smem_raw + 16);
@@ -92,38 +93,40 @@ __global__ void __launch_bounds__(NW * 32, 4) decode_bytes_kernel(TileArgs A) {
   T.b = tile_b;
   asm volatile("mov.u32 %0, %1;" : "=r"(T.s) : "r"(smem_u32(tile_b)) : "memory");   // ordered after mbar_wait
 
-  // ---- CRC of the 32 payloads, shared by all warps (see crc_chunks in tile.cuh) ----
-  const bool on = active && A.verify;
-  const uint32_t hn = min(len, (0u - pay) & 15u);
-  const uint32_t b0 = pay + hn;
-  const uint32_t K = (end - b0) >> 4;
-  if (on) {
-    uint32_t c = 0;
-    if (wid == 0) {
-      c = 0xFFFFFFFFu;
-      for (uint32_t i = 0; i < hn; ++i) c = crc_byte(s8, c, T.u8(pay + i));
-    }
-    if (wid == NW - 1) {       // the frame index chained the headers without checking them: the length CRC
-      if (crc_mask(~crc_fold8(s8, 0xFFFFFFFFu, t_u32(T, pay - 12), t_u32(T, pay - 8))) != t_u32(T, pay - 4)) atomicOr(A.flags, TF_FALLBACK);
-    }
-    const uint32_t k0 = K * wid / NW, k1 = K * (wid + 1) / NW;
-    if (k1 > k0 || wid == 0) {
+  if (wid < CW) {
+    // ---- CRC of the 32 payloads, shared by the CRC warps (see crc_chunks in tile.cuh) ----
+    const bool on = active && A.verify;
+    const uint32_t hn = min(len, (0u - pay) & 15u);
+    const uint32_t b0 = pay + hn;
+    const uint32_t K = (end - b0) >> 4;
+    if (on) {
+      uint32_t c = 0;
+      if (wid == 0) {
+        c = 0xFFFFFFFFu;
+        for (uint32_t i = 0; i < hn; ++i) c = crc_byte(s8, c, T.u8(pay + i));
+      }
+      if (wid == CW - 1) {       // the frame index chained the headers without checking them: the length CRC
+        if (crc_mask(~crc_fold8(s8, 0xFFFFFFFFu, t_u32(T, pay - 12), t_u32(T, pay - 8))) != t_u32(T, pay - 4)) atomicOr(A.flags, TF_FALLBACK);
+      }
+      const uint32_t k0 = K * wid / CW, k1 = K * (wid + 1) / CW;
       c = crc_chunks(s8, T, b0 + 16 * k0, k1 - k0, c);
-      if (c) atomicXor(&scrc[lane], K - k1 ? gf2_mulmod(xp16[K - k1], c) : c);
+      if (CW == 1) scrc[lane] = c;
+      else if (c) atomicXor(&scrc[lane], K - k1 ? gf2_mulmod(xp16[K - k1], c) : c);
     }
-  }
-  __syncthreads();
-  if (wid == 0 && on) {
-    uint32_t c = scrc[lane];
-    for (uint32_t o = b0 + 16 * K; o < end; ++o) c = crc_byte(s8, c, T.u8(o));
-    if (crc_mask(~c) != t_u32(T, end)) atomicOr(A.flags, TF_FALLBACK);          // the general path reports the error at the right record
+    if (CW > 1) asm volatile("bar.sync 1, %0;" ::"r"(CW * 32) : "memory");
+    if (wid == 0 && on) {
+      uint32_t c = scrc[lane];
+      for (uint32_t o = b0 + 16 * K; o < end; ++o) c = crc_byte(s8, c, T.u8(o));
+      if (crc_mask(~c) != t_u32(T, end)) atomicOr(A.flags, TF_FALLBACK);          // the general path reports the error at the right record
+    }
+    return;
   }
 
   // ---- rows out: bytes [pre, pre + len) of the values buffer, offsets[row] = pre ----
   const uint32_t pre = off - 16u * row;                                          // payload bytes of the rows before this one (rec_off[0] == 0)
   uint8_t* values = reinterpret_cast<uint8_t*>(A.var_values[0]);
   int32_t* offs = A.offs[0];
-  if (wid == 1 % NW) {
+  if (wid == CW) {
     if (active) offs[row] = (int32_t)pre;
     if (lane == 0) reinterpret_cast<uint32_t*>(A.bitmaps)[tile] = rows == TILE_ROWS ? 0xFFFFFFFFu : (1u << rows) - 1u;      // every row is valid
     if (row0 + rows == n_rows && lane == 0) {
@@ -133,7 +136,16 @@ __global__ void __launch_bounds__(NW * 32, 4) decode_bytes_kernel(TileArgs A) {
       if (A.cap && total > A.cap[0]) atomicOr(A.flags, TF_OVERFLOW | TF_FALLBACK);   // (cannot happen: the host sizes the buffer from the input's size)
     }
   }
-  for (uint32_t r = wid; r < rows; r += NW) {
+  if (wid == CW + XW - 1 && A.pf_dist) {
+    // the tile that takes this CTA's place when it retires: ask L2 for its records now (see decode_tile_kernel)
+    const uint32_t row2 = (tile + A.pf_dist) * TILE_ROWS + lane;
+    if (row2 < n_rows) {
+      const uint32_t o2 = A.rec_off[row2] + mis, e2 = min(A.rec_off[row2 + 1] + mis, lim & ~15u);
+      const uint32_t a2 = (o2 + 15u) & ~15u;
+      if (e2 > a2 + 16u) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(base + a2), "r"((e2 - a2) & ~15u) : "memory");
+    }
+  }
+  for (uint32_t r = wid - CW; r < rows; r += XW) {
     const uint32_t spay = __shfl_sync(FULLMASK, pay, r), slen = __shfl_sync(FULLMASK, len, r), spre = __shfl_sync(FULLMASK, pre, r);
     uint8_t* dst = values + spre;
     const uint32_t hm = min(slen, (0u - (uint32_t)reinterpret_cast<uintptr_t>(dst)) & 3u);

@@ -1,5 +1,5 @@
 """quick device-resident timing of the pipelined decode (developer tool; bench.py is the measurement of record)
-usage: quick_resident.py MIB STEPS [cfg2|ragged|strings]"""
+usage: quick_resident.py MIB STEPS [cfg2|ragged|strings|seq|bytes]"""
 import os, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
@@ -11,6 +11,7 @@ from spark_tfrecord_b200 import _native
 mib = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
 steps = int(sys.argv[2]) if len(sys.argv) > 2 else 200
 kind = sys.argv[3] if len(sys.argv) > 3 else "cfg2"
+RT = {"seq": 1, "bytes": 2}.get(kind, 0)
 if kind == "cfg2":
     schema, n, dev, batches = bench.make_device_pool(mib, 2, seed=2024, device=0, keep_host=2)
 else:
@@ -21,18 +22,26 @@ else:
         from oracle.corpus import cfg4_columns          # developer tool only
         n = (mib << 20) // 1650
         mk = lambda seed: cfg4_columns(n, seed=seed)
-    else:
+    elif kind == "strings":
         from oracle.corpus import cfg1_columns          # developer tool only: 4 long, 4 float, 2 string columns, ~220-byte records
         n = (mib << 20) // 220
         mk = lambda seed: cfg1_columns(n, seed=seed)
+    elif kind == "bytes":
+        from spark_tfrecord_b200._cabi import HostColumn
+        from spark_tfrecord_b200.sqltypes import byte_array_schema, TFR_T_BINARY
+        n = (mib << 20) // 1040
+        def mk(seed):
+            rng = np.random.default_rng(seed)
+            return byte_array_schema(), [HostColumn(TFR_T_BINARY, 0, n, np.full((n + 7) // 8, 0xFF, np.uint8), [(np.arange(n + 1, dtype=np.int64) * 1024).astype(np.int32)],
+                                                    rng.integers(0, 256, n * 1024, dtype=np.uint8))]
     dev, batches = [], []
     for i in range(2):
         schema, cols = mk(100 + i)
-        enc = _native.Encoder(schema, 1 if kind == "seq" else 0, 0)
+        enc = _native.Encoder(schema, RT, 0)
         data = np.frombuffer(enc.encode(cols), dtype=np.uint8)
         enc.close()
         batches.append(data); dev.append(torch.from_numpy(data.copy()).cuda())
-dec = _native.Decoder(schema, 1 if kind == "seq" else 0)
+dec = _native.Decoder(schema, RT)
 for i in range(4):
     b, used = dec.decode(dev[i % 2]); assert b.info["error_code"] == 0; b.release()
 stream = torch.cuda.ExternalStream(dec.stream())
