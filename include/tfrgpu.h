@@ -179,6 +179,13 @@ typedef struct tfr_batch_info {
   int32_t frame_repairs;   /* chunks whose speculative boundary had to be re-chained       */
 } tfr_batch_info;
 int32_t tfr_batch_status(tfr_batch*, tfr_batch_info* out);
+/* Bytes of the submitted block this batch consumes, available as soon as the batch's frame index has run -- before its
+ * rows are decoded.  The block loop of a streaming reader (TFRecordFileReader.scala:49-61: records are read one after
+ * the other, so block t+1 starts where block t's last complete record ended) calls this right after tfr_decode_submit,
+ * cuts and submits the next block, and only then waits for this one's rows: the decode of block t runs under the frame
+ * index of block t+1.  For a batch that later reports an error, tfr_batch_info.consumed_bytes (the bytes in front of the
+ * failing record) is what counts; the reader stops there anyway.                                                     */
+int32_t tfr_batch_consumed(tfr_batch*, size_t* consumed);
 
 /* One output column in Arrow layout.  n_levels offset arrays (int32, Arrow list/binary
  * offsets) from the outermost (one entry per row + 1) to the innermost, then the leaf

@@ -23,7 +23,7 @@ EXPORTS = [
     "tfr_abi_version", "tfr_status_string", "tfr_last_error", "tfr_schema_create", "tfr_schema_destroy",
     "tfr_schema_num_fields", "tfr_decoder_create", "tfr_decoder_destroy", "tfr_decoder_staging", "tfr_decoder_staging_slot",
     "tfr_decoder_num_staging_slots", "tfr_decode", "tfr_decode_submit",
-    "tfr_decoder_stream", "tfr_decoder_set_profiling", "tfr_decoder_get_profile", "tfr_decoder_get_stats", "tfr_batch_wait", "tfr_batch_status", "tfr_batch_num_columns", "tfr_batch_columns",
+    "tfr_decoder_stream", "tfr_decoder_set_profiling", "tfr_decoder_get_profile", "tfr_decoder_get_stats", "tfr_batch_wait", "tfr_batch_status", "tfr_batch_consumed", "tfr_batch_num_columns", "tfr_batch_columns",
     "tfr_batch_to_host_async", "tfr_batch_to_host", "tfr_batch_export_arrow_host", "tfr_batch_export_arrow_device", "tfr_batch_release",
     "tfr_encoder_create", "tfr_encoder_destroy", "tfr_encode", "tfr_encoder_result_host", "tfr_encoder_stream",
     "tfr_infer_create", "tfr_infer_update", "tfr_infer_update_block", "tfr_infer_result", "tfr_infer_name", "tfr_infer_destroy",
@@ -116,6 +116,7 @@ def lib():
         "tfr_decoder_get_profile": (i32, [vp, P(C.c_double), P(i64), P(i64)]),
         "tfr_batch_wait": (i32, [vp]),
         "tfr_batch_status": (i32, [vp, P(tfr_batch_info)]),
+        "tfr_batch_consumed": (i32, [vp, P(C.c_size_t)]),
         "tfr_batch_num_columns": (i32, [vp]),
         "tfr_batch_columns": (i32, [vp, P(tfr_column), i32]),
         "tfr_batch_to_host": (i32, [vp, P(tfr_column), i32]),
@@ -212,6 +213,12 @@ class Batch:
 
     def wait(self):
         _check(lib().tfr_batch_wait(self.h))
+
+    def consumed(self) -> int:
+        """bytes of the submitted block this batch consumes: known once the frame index has run, before the rows are decoded"""
+        n = C.c_size_t()
+        _check(lib().tfr_batch_consumed(self.h, C.byref(n)))
+        return n.value
 
     def to_host_async(self):
         """enqueue the D2H of every Arrow buffer behind the batch's kernels (overlaps the next batch)"""

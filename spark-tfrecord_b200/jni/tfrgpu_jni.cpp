@@ -107,6 +107,13 @@ extern "C" JNIEXPORT void JNICALL Java_com_linkedin_spark_datasources_tfrecord_T
   int32_t rc = tfr_batch_to_host_async((tfr_batch*)batch);
   if (rc) { tfr_batch_release((tfr_batch*)batch); throw_for(env, rc, -1); }
 }
+// where the block after this one starts: known after the batch's frame index, before its rows (the reader submits the next block first)
+extern "C" JNIEXPORT jlong JNICALL Java_com_linkedin_spark_datasources_tfrecord_TfrGpu_batchConsumed(JNIEnv* env, jclass, jlong batch) {
+  size_t used = 0;
+  int32_t rc = tfr_batch_consumed((tfr_batch*)batch, &used);
+  if (rc) { tfr_batch_release((tfr_batch*)batch); throw_for(env, rc, -1); return 0; }
+  return (jlong)used;
+}
 extern "C" JNIEXPORT jlongArray JNICALL Java_com_linkedin_spark_datasources_tfrecord_TfrGpu_batchStatus(JNIEnv* env, jclass, jlong batch) {
   tfr_batch_info i{};
   int32_t rc0 = tfr_batch_status((tfr_batch*)batch, &i);

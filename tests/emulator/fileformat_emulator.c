@@ -170,24 +170,27 @@ static void reader_open(Reader* R, const char* path, size_t block) { /* buildRea
   R->carry_cap = 1 << 16; R->carry = malloc(R->carry_cap);
   reader_submit_next(R);
 }
-/* make the submitted block the current one: wait, fetch host columns, keep its tail, submit the block after it */
+/* make the submitted block the current one.  Where it ends is known as soon as its frame index has run (tfr_batch_consumed):
+ * its tail is carried over and the block after it is submitted BEFORE this one's rows are waited for, so the next block's
+ * copy and frame index overlap this block's decode and the consumption of its rows */
 static void reader_advance(Reader* R) {
   if (R->cur) { tfr_batch_release(R->cur); R->cur = NULL; }
   if (!R->ahead) { R->finished = 1; return; }
   tfr_batch* b = R->ahead; R->ahead = NULL;
-  tfr_batch_info info;
-  OK(tfr_batch_status(b, &info));                                    /* waits for the pipelined batch; consumed_bytes is final */
-  OK(tfr_batch_to_host(b, R->cols, N_FIELDS));
-  R->cur = b; R->cur_row = 0; R->cur_rows = info.n_rows; R->cur_err = info.error_code; R->cur_err_row = info.error_row;
-  if (info.error_code == 0 && !R->ahead_final) {
-    /* carry the partial record: it sits in the staging slot behind consumed_bytes */
+  if (!R->ahead_final) {
+    size_t used = 0;
+    OK(tfr_batch_consumed(b, &used));
     void* st = NULL; size_t cap = 0;
     OK(tfr_decoder_staging_slot(R->dec, R->ahead_slot, 0, &st, &cap));
-    R->carry_len = R->ahead_nbytes - (size_t)info.consumed_bytes;
+    R->carry_len = R->ahead_nbytes - used;                            /* the partial record sits in the staging slot behind `used` */
     if (R->carry_len > R->carry_cap) { R->carry_cap = R->carry_len * 2; R->carry = realloc(R->carry, R->carry_cap); }
-    memcpy(R->carry, (uint8_t*)st + info.consumed_bytes, R->carry_len);
-    reader_submit_next(R);                                           /* the next block decodes while this one's rows are consumed */
+    memcpy(R->carry, (uint8_t*)st + used, R->carry_len);
+    reader_submit_next(R);
   }
+  tfr_batch_info info;
+  OK(tfr_batch_status(b, &info));                                    /* waits for the rows; with an error, consumed_bytes is the final word and the stream ends here */
+  OK(tfr_batch_to_host(b, R->cols, N_FIELDS));
+  R->cur = b; R->cur_row = 0; R->cur_rows = info.n_rows; R->cur_err = info.error_code; R->cur_err_row = info.error_row;
 }
 /* Iterator.hasNext / next fused: 1 = a row was delivered into *h, 0 = end of file, < 0 = the status the reference would throw for */
 static int32_t reader_next(Reader* R, uint64_t* h) {

@@ -601,3 +601,55 @@ def test_bytearray_exact_end_buffer(native, oracle):
         dec.close()
         for p in ptrs:
             rt.cudaFree(p)
+
+
+def test_consumed_is_known_before_the_rows(native, oracle):
+    """tfr_batch_consumed: a streaming reader cuts block t+1 from block t's consumed count right after submitting it, with block t
+    still in flight (M/TFRecordFileReader.scala:49-61 reads record after record; a block boundary is wherever the last complete
+    record ends).  Every block's early count must equal its final consumed_bytes and the rows of all blocks together must be
+    the file's rows; a corrupt record ends the stream with the oracle's error at the oracle's row."""
+    import torch
+    from oracle.corpus import cfg2_columns
+    sch, cols = cfg2_columns(60000, seed=31)
+    data = _encode(oracle, sch, cols)
+    offs = record_offsets(data)
+    d_data = torch.from_numpy(data.copy()).cuda()
+    dec = native.Decoder(sch)
+    try:
+        for block in (7 << 20, 3_333_333):
+            pos, row0, inflight = 0, 0, []
+            while pos < len(data):
+                take = min(block, len(data) - pos)
+                final = pos + take == len(data)
+                b = dec.submit((d_data.data_ptr() + pos, take, 1), is_final=final)
+                used = b.consumed()                          # before anything else is asked of the batch
+                want_used = int(offs[np.searchsorted(offs, pos + take, side="right") - 1]) - pos
+                assert used == want_used, (pos, take, used, want_used)
+                inflight.append((b, pos, used))
+                pos += used
+                if len(inflight) == 3:
+                    ob, p0, u0 = inflight.pop(0)
+                    assert ob.info["error_code"] == 0 and ob.info["consumed_bytes"] == u0, ob.info
+                    r1 = row0 + ob.n_rows
+                    assert_columns_equal(ob.to_host(), slice_columns(cols, row0, r1), sch.names, f"block at {p0}")
+                    row0 = r1
+                    ob.release()
+            for ob, p0, u0 in inflight:
+                assert ob.info["error_code"] == 0 and ob.info["consumed_bytes"] == u0, ob.info
+                r1 = row0 + ob.n_rows
+                assert_columns_equal(ob.to_host(), slice_columns(cols, row0, r1), sch.names, f"block at {p0}")
+                row0 = r1
+                ob.release()
+            assert row0 == 60000
+        assert dec.stats()["speculative_submits"] > 10
+        # a flipped payload byte in record 40000: the block that holds it reports the error; its final consumed count stops in front of the record
+        bad = data.copy(); bad[offs[40000] + 100] ^= 1
+        d_bad = torch.from_numpy(bad).cuda()
+        b = dec.submit((d_bad.data_ptr() + int(offs[39000]), int(offs[41000] - offs[39000]), 1), is_final=True)
+        early = b.consumed()
+        assert early == int(offs[41000] - offs[39000])
+        assert b.info["error_code"] == A.TFR_E_CRC_DATA and b.info["error_row"] == 1000 and b.info["consumed_bytes"] == int(offs[40000] - offs[39000]), b.info
+        assert b.consumed() == b.info["consumed_bytes"]          # resolved: the final word
+        b.release()
+    finally:
+        dec.close()

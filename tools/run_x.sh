@@ -1,6 +1,12 @@
 mkdir -p gpurun_out
-for cw in 8 10 12 16; do echo "cw $cw"; TFR_BYTES_CW=$cw timeout 300 python tools/quick_resident.py 1024 100 bytes 2>&1 | grep submit | cut -c1-200; done
-echo "cw 8 nofill"; TFR_BYTES_NOFILL=1 TFR_BYTES_CW=8 timeout 300 python tools/quick_resident.py 1024 100 bytes 2>&1 | grep submit | cut -c1-200
-echo "cw 12 nofill"; TFR_BYTES_NOFILL=1 TFR_BYTES_CW=12 timeout 300 python tools/quick_resident.py 1024 100 bytes 2>&1 | grep submit | cut -c1-200
-echo "cw 8 noprefetch"; TFR_NO_L2_PREFETCH=1 TFR_BYTES_CW=8 timeout 300 python tools/quick_resident.py 1024 100 bytes 2>&1 | grep submit | cut -c1-200
-TFR_BYTES_CW=8 timeout 300 ncu --set full --clock-control none --import-source on -k regex:decode_bytes -s 6 -c 1 -f -o gpurun_out/r2_x_bytes_tile python tools/quick_resident.py 1024 4 bytes > gpurun_out/x_bytes_ncu.log 2>&1
+timeout 900 python -m pytest tests -q -m gpu -x > gpurun_out/x_tests.txt 2>&1
+tail -4 gpurun_out/x_tests.txt
+timeout 900 python bench.py --pool 4 --batches-per-step 16 --steps 4 --no-cpu --no-parity --cfg5-passes 1 > gpurun_out/x_bench.json 2> gpurun_out/x_bench.err
+tail -3 gpurun_out/x_bench.err
+python - <<'PY'
+import json
+d=json.loads(open('gpurun_out/x_bench.json').read().strip().split('\n')[-1])
+print(d['value'], d['e2e']['value'], d['e2e'].get('one_handle_one_thread'), d['e2e'].get('two_handles_two_threads'))
+print({k:(round(v['value'],1), round(v['ms_per_batch'],3)) for k,v in d['extra'].items()})
+print(d['cfg5_file_sharded']['value'], d['cfg5_file_sharded'].get('blocks'))
+PY
