@@ -260,7 +260,7 @@ __host__ __device__ inline uint32_t tile_schema_smem(uint32_t nf, uint32_t names
 }
 __host__ __device__ inline uint32_t tile_const_bytes(uint32_t nf, uint32_t names_bytes) { return TILE_CRC_BYTES + TILE_SEEN_BYTES + tile_schema_smem(nf, names_bytes); }
 // ragged mode scratch behind the tile: cell source offsets [n_var][32] | per-array counts -> local offsets [n_cnt][32] | totals [n_cnt] | bases u64 [n_cnt] | tile id
-__host__ __device__ inline uint32_t tile_ragged_bytes(uint32_t n_var, uint32_t n_cnt) { return (n_var + n_cnt) * 128u + n_cnt * 4u + n_cnt * 8u + 16u + 16u + 64u; }
+__host__ __device__ inline uint32_t tile_ragged_bytes(uint32_t n_var, uint32_t n_cnt) { return (n_var + n_cnt) * 128u + n_cnt * 4u + n_cnt * 8u + 16u + 16u + 96u; }
 #define TILE_SQ_STEPS 128u       // FeatureList steps per record the one-pass mode keeps per-step element counts for
 // SequenceExample scratch: FeatureList count sums [n_var][32][2] u32, then (one-pass mode, at most 4 variable-width columns)
 // the per-step element counts [n_var][TILE_SQ_STEPS][32] u8
@@ -277,7 +277,7 @@ __host__ __device__ inline uint32_t tile_smem_bytes(uint32_t nf, uint32_t names_
 // Merely containing those calls costs the kernel 7 % (474 vs 510 GB/s on ragged configs[1], never executing them), so the
 // default instantiation has none: it raises TF_XCODE instead and the host re-runs the batch -- and the next ones -- with XC.
 template <bool SEQ, bool RG, int PW, int CW, bool XC>
-__global__ void __launch_bounds__((PW + CW) * 32, (PW >= 12 ? TILE_MIN_CTAS : 8)) decode_tile_kernel(TileArgs A) {
+__global__ void __launch_bounds__((PW + CW) * 32, (PW >= 16 ? 2 : PW >= 12 ? TILE_MIN_CTAS : 8)) decode_tile_kernel(TileArgs A) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
   uint32_t* s8 = reinterpret_cast<uint32_t*>(smem_raw + 16);                               // g5 tables, then xp16
@@ -296,8 +296,8 @@ __global__ void __launch_bounds__((PW + CW) * 32, (PW >= 12 ? TILE_MIN_CTAS : 8)
   uint32_t* rg_src = reinterpret_cast<uint32_t*>(tile_b + A.tile_cap + 64);           // [n_var][32] tile offset of each cell's bytes
   uint32_t* rg_cnt = rg_src + (uint32_t)A.sch.n_var * 32u;                            // [n_cnt][32] counts, then tile-local exclusive offsets
   uint32_t* rg_tot = rg_cnt + A.n_cnt * 32u;                                          // [n_cnt] tile totals
-  unsigned long long* rg_base = reinterpret_cast<unsigned long long*>(rg_tot + ((A.n_cnt + 1u) & ~1u) + 16u);  // [n_cnt] exclusive bases of this tile
-  uint32_t* rg_tile = rg_tot + ((A.n_cnt + 1u) & ~1u);                                // [0] tile id, [1] skip-copy flag, [2..14) look-back summaries of the warps
+  unsigned long long* rg_base = reinterpret_cast<unsigned long long*>(rg_tot + ((A.n_cnt + 1u) & ~1u) + 24u);  // [n_cnt] exclusive bases of this tile
+  uint32_t* rg_tile = rg_tot + ((A.n_cnt + 1u) & ~1u);                                // [0] tile id, [1] skip-copy flag, [2..2+PW] look-back summaries of the parse warps + the give-up word (PW <= 16)
   // SequenceExample: per (column, row) element / byte counts of the FeatureLists, summed over the parse warps [n_var][32][2]
   uint32_t* sq_cnt = reinterpret_cast<uint32_t*>(tile_b + A.tile_cap + 64 + (RG ? tile_ragged_bytes((uint32_t)A.sch.n_var, A.n_cnt) : 0u));
   uint8_t* sq_tab = reinterpret_cast<uint8_t*>(sq_cnt + (uint32_t)A.sch.n_var * 64u + 4u);      // [n_var][TILE_SQ_STEPS][32] elements per step (SEQ && RG)
