@@ -256,36 +256,51 @@ class TFRecordFileReader:
     @staticmethod
     def readFile(conf, options: Dict[str, str], file: PartitionedFile, schema: StructType, device: int = 0,
                  block_bytes: Optional[int] = None) -> Iterator[tuple]:
-        """Stages the file in blocks into the decoder's pinned buffer and decodes each block on the GPU; the
-        unconsumed tail of a block (a partial record) is carried into the next one.  Rows before a bad
-        record are yielded, then the exception the reference would throw is raised."""
+        """Stages the file in blocks into the decoder's pinned staging slots and decodes each block on the GPU
+        (tfr_decode_submit); where a block ends -- the carry into the next one -- is known as soon as its frame index has
+        run (tfr_batch_consumed), so block k+1 is read and submitted while block k decodes and block k-1's rows are
+        handed out.  Rows before a bad record are yielded, then the exception the reference would throw is raised."""
         rt = _record_type(options)
         block = block_bytes or TFRecordFileReader.BLOCK_BYTES
         dec = _native.Decoder(schema, rt, device, TFR_F_DEFAULT)
 
         def gen():
+            todo = []
             try:
                 compressed = _codec_of_path(file.toPath()) is not None
                 with _open_read(file.toPath()) as f:
                     if not compressed:
                         f.seek(file.start)
                     remaining = (1 << 62) if compressed else file.length          # a compressed file is read to its end
-                    todo = []
+                    n_slots = dec.num_staging_slots()
+                    turn = [0]
+
+                    def stage(nbytes):
+                        st = dec.staging_slot(turn[0] % n_slots, nbytes)
+                        turn[0] += 1
+                        return st
 
                     def process(st, nbytes, final):
-                        batch, used = dec.decode(st, is_final=final, nbytes=nbytes)
+                        batch = dec.submit(st, is_final=final, nbytes=nbytes)
                         todo.append(batch)
-                        return used
+                        return batch.consumed()
 
-                    for _ in _stream_blocks(f, remaining, block, dec.staging, process):
-                        batch = todo.pop()
+                    def drain(batch):
                         try:
                             for row in _rows_of(batch):
                                 yield row
                             batch.raise_if_error()
                         finally:
                             batch.release()
+
+                    for _ in _stream_blocks(f, remaining, block, stage, process):
+                        while len(todo) > 1:                 # the block before the one just submitted
+                            yield from drain(todo.pop(0))
+                    while todo:
+                        yield from drain(todo.pop(0))
             finally:
+                for batch in todo:
+                    batch.release()
                 dec.close()
 
         return gen()
