@@ -35,11 +35,17 @@ struct EncTileArgs {
   const int32_t* rec_off;       // [n_rows+1]
   uint8_t* out;
   uint32_t slot;                // bytes per record slot, 4 (mod 128)
+  uint32_t names_bytes;         // bytes of sch.names (staged in shared memory by encode_tile_kernel)
 };
 
 // shared memory: g5 + xp16 (4 KiB) | CRC accumulators [32] | group size [32] | vsz u16 [nf][32] | eoff u16 [nf][32] | slots
 __host__ __device__ inline uint32_t enc_tile_smem_bytes(uint32_t nf, uint32_t slot) {
   return 4096 + 128 + 128 + ((nf * 32 * 2 * 2 + 15u) & ~15u) + ENC_TILE_ROWS * slot + 16;
+}
+// encode_tile_kernel also keeps the schema's fields, the column pointers and the names in shared memory (in front of the slots):
+// per (field, row) only the value loads go to global memory, not a chain fields[f] -> cols[f] -> values
+__host__ __device__ inline uint32_t enc_tile_meta_bytes(uint32_t nf, uint32_t names_bytes) {
+  return ((nf * (uint32_t)sizeof(DevField) + 15u) & ~15u) + ((nf * (uint32_t)sizeof(EncCol) + 15u) & ~15u) + ((names_bytes + 15u) & ~15u);
 }
 
 // size pass with the same mapping (lane = row, warp w takes fields w, w+W, ...): coalesced column reads, Feature sizes
@@ -90,7 +96,11 @@ __global__ void __launch_bounds__(ENC_TILE_THREADS, 3) encode_tile_kernel(EncTil
   const uint32_t nf = (uint32_t)A.sch.n_fields;
   uint16_t* vsz = reinterpret_cast<uint16_t*>(sgrp + 32);
   uint16_t* eoff = vsz + nf * 32;
-  uint8_t* slots = esm + 4096 + 128 + 128 + ((nf * 32 * 2 * 2 + 15u) & ~15u);
+  uint8_t* meta = esm + 4096 + 128 + 128 + ((nf * 32 * 2 * 2 + 15u) & ~15u);
+  DevField* sfd = reinterpret_cast<DevField*>(meta);
+  EncCol* scol = reinterpret_cast<EncCol*>(meta + ((nf * (uint32_t)sizeof(DevField) + 15u) & ~15u));
+  uint8_t* snames = meta + ((nf * (uint32_t)sizeof(DevField) + 15u) & ~15u) + ((nf * (uint32_t)sizeof(EncCol) + 15u) & ~15u);
+  uint8_t* slots = meta + enc_tile_meta_bytes(nf, A.names_bytes);
   const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const uint32_t row0 = blockIdx.x * ENC_TILE_ROWS;
   const uint32_t rows = min((uint32_t)ENC_TILE_ROWS, A.n_rows - row0);
@@ -101,6 +111,15 @@ __global__ void __launch_bounds__(ENC_TILE_THREADS, 3) encode_tile_kernel(EncTil
     const uint32_t* g = A.tabs->g5;
     for (uint32_t i = threadIdx.x; i < 1024; i += ENC_TILE_THREADS) g5[i] = g[i];
     if (threadIdx.x < 32) scrc[threadIdx.x] = 0;
+    {
+      const uint32_t* gf = reinterpret_cast<const uint32_t*>(A.sch.fields);          // DevField and EncCol are whole words
+      uint32_t* df = reinterpret_cast<uint32_t*>(sfd);
+      for (uint32_t i = threadIdx.x; i < nf * (uint32_t)(sizeof(DevField) / 4); i += ENC_TILE_THREADS) df[i] = gf[i];
+      const uint32_t* gc = reinterpret_cast<const uint32_t*>(A.cols);
+      uint32_t* dc = reinterpret_cast<uint32_t*>(scol);
+      for (uint32_t i = threadIdx.x; i < nf * (uint32_t)(sizeof(EncCol) / 4); i += ENC_TILE_THREADS) dc[i] = gc[i];
+      for (uint32_t i = threadIdx.x; i < A.names_bytes; i += ENC_TILE_THREADS) snames[i] = A.sch.names[i];
+    }
     for (uint32_t f = wid; f < nf; f += ENC_TILE_WARPS) {
       const uint32_t V = active ? A.cell_size[(size_t)f * A.n_rows + row] : 0xffffffffu;
       vsz[f * 32 + lane] = V == 0xffffffffu ? (uint16_t)0xffff : (uint16_t)V;
@@ -112,7 +131,7 @@ __global__ void __launch_bounds__(ENC_TILE_THREADS, 3) encode_tile_kernel(EncTil
     for (uint32_t f = 0; f < nf; ++f) {
       const uint32_t V = vsz[f * 32 + lane];
       eoff[f * 32 + lane] = (uint16_t)acc;
-      if (V != 0xffffu) acc += entry_total(A.sch.fields[f], V);
+      if (V != 0xffffu) acc += entry_total(sfd[f], V);
     }
     sgrp[lane] = acc;
   }
@@ -126,13 +145,13 @@ __global__ void __launch_bounds__(ENC_TILE_THREADS, 3) encode_tile_kernel(EncTil
     for (uint32_t f = wid; f < nf; f += ENC_TILE_WARPS) {
       const uint32_t V = vsz[f * 32 + lane];
       if (V == 0xffffu) continue;                                  // null: the feature is omitted (:29)
-      const DevField& fd = A.sch.fields[f];
-      const EncCol& c = A.cols[f];
+      const DevField& fd = sfd[f];
+      const EncCol& c = scol[f];
       uint8_t* p = rec + 12 + ghdr + eoff[f * 32 + lane];
       const uint32_t E = 1 + vsize32(fd.name_len) + fd.name_len + 1 + vsize32(V) + V;
       *p++ = 0x0A; p = put_varint(p, E);
       *p++ = 0x0A; p = put_varint(p, fd.name_len);
-      const uint8_t* nm = A.sch.names + fd.name_off;
+      const uint8_t* nm = snames + fd.name_off;
       for (uint32_t k = 0; k < fd.name_len; ++k) p[k] = nm[k];
       p += fd.name_len;
       *p++ = 0x12; p = put_varint(p, V);
@@ -174,12 +193,20 @@ __global__ void __launch_bounds__(ENC_TILE_THREADS, 3) encode_tile_kernel(EncTil
     for (int i = 0; i < 4; ++i) ft[i] = (uint8_t)(fc >> (8 * i));
   }
   __syncthreads();
-  // ---- copy-out: whole records, 32 consecutive bytes per instruction ----
+  // ---- copy-out: whole records, 128 consecutive bytes per instruction (the output position decides the word alignment) ----
   for (uint32_t r = wid; r < rows; r += ENC_TILE_WARPS) {
     const uint32_t g0 = (uint32_t)A.rec_off[row0 + r], flen = (uint32_t)A.rec_off[row0 + r + 1] - g0;
-    const uint8_t* s = slots + r * A.slot;
+    const uint32_t s0 = r * A.slot;                                // 4-byte aligned
     uint8_t* d = A.out + g0;
-    for (uint32_t i = lane; i < flen; i += 32) d[i] = s[i];
+    const uint32_t hm = min(flen, (0u - (uint32_t)reinterpret_cast<uintptr_t>(d)) & 3u);
+    if (lane < hm) d[lane] = (uint8_t)T.u8(s0 + lane);
+    const uint32_t words = (flen - hm) >> 2;
+    const uint32_t so = s0 + hm, sh = (so & 3u) * 8u, sa = so & ~3u;
+    uint32_t* dw = reinterpret_cast<uint32_t*>(d + hm);
+    if (sh == 0) for (uint32_t i = lane; i < words; i += 32) dw[i] = T.w32(sa + 4 * i);
+    else for (uint32_t i = lane; i < words; i += 32) dw[i] = __funnelshift_r(T.w32(sa + 4 * i), T.w32(sa + 4 * i + 4), sh);   // (reads at most 3 bytes past the record: inside its slot)
+    const uint32_t tl = (flen - hm) & 3u;
+    if (lane < tl) d[hm + 4 * words + lane] = (uint8_t)T.u8(so + 4 * words + lane);
   }
 }
 

@@ -49,7 +49,7 @@ print("samples", tot, "warp instructions", ti)
 lines = {}
 for k, n in sorted(samp.items(), key=lambda x: -x[1])[:top]:
     text = ""
-    if k and k[0] in ("tile.cuh", "common.cuh", "decode.cuh", "encode_tile.cuh", "frame.cuh"):
+    if k and k[0] in ("tile.cuh", "common.cuh", "decode.cuh", "encode_tile.cuh", "frame.cuh", "bytes_tile.cuh", "encode.cuh"):
         f = os.path.join(root, "spark-tfrecord_b200", "csrc", k[0])
         lines.setdefault(f, open(f).read().split("\n"))
         text = lines[f][k[1] - 1].strip()[:110]

@@ -1,12 +1,11 @@
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests -q -m gpu -x > gpurun_out/x_tests.txt 2>&1
-tail -4 gpurun_out/x_tests.txt
-timeout 900 python bench.py --pool 4 --batches-per-step 16 --steps 4 --no-cpu --no-parity --cfg5-passes 1 > gpurun_out/x_bench.json 2> gpurun_out/x_bench.err
-tail -3 gpurun_out/x_bench.err
+timeout 300 python tools/quick_encode.py 256 20
+timeout 300 python tools/quick_encode.py 1024 10
+timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -s 40 -c 24 --csv --log-file gpurun_out/x_enc_launches.csv python tools/quick_encode.py 256 8 > /dev/null 2>&1
 python - <<'PY'
-import json
-d=json.loads(open('gpurun_out/x_bench.json').read().strip().split('\n')[-1])
-print(d['value'], d['e2e']['value'], d['e2e'].get('one_handle_one_thread'), d['e2e'].get('two_handles_two_threads'))
-print({k:(round(v['value'],1), round(v['ms_per_batch'],3)) for k,v in d['extra'].items()})
-print(d['cfg5_file_sharded']['value'], d['cfg5_file_sharded'].get('blocks'))
+import csv
+for r in csv.reader(open('gpurun_out/x_enc_launches.csv')):
+    if len(r)>10 and r[0].isdigit(): print(r[0], r[4].split('(')[0][:50], r[8], r[7], r[-1])
 PY
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:encode_tile_kernel -s 4 -c 1 -f -o gpurun_out/r2_x_encode_tile python tools/quick_encode.py 256 4 > gpurun_out/x_enc_ncu.log 2>&1
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:encode_tile_size -s 4 -c 1 -f -o gpurun_out/r2_x_encode_size python tools/quick_encode.py 256 4 > gpurun_out/x_enc_ncu2.log 2>&1
