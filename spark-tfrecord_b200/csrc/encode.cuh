@@ -87,9 +87,11 @@ __device__ __forceinline__ uint8_t* emit_list_body(uint8_t* p, const DevField& f
   }
   if (fd.kind == K_FLOAT) {
     *p++ = 0x0A; p = put_varint(p, 4ull * n);
+    const bool aligned = (reinterpret_cast<uintptr_t>(p) & 3u) == 0;            // whole-word stores when the packed floats happen to start on a word
     for (int32_t i = lo; i < hi; ++i) {
       uint32_t b = fd.elem_type == TFR_T_FLOAT32 ? ((const uint32_t*)c.values)[i] : double_to_float_bits(((const double*)c.values)[i]);   // toFloat (:86,113)
-      p[0] = (uint8_t)b; p[1] = (uint8_t)(b >> 8); p[2] = (uint8_t)(b >> 16); p[3] = (uint8_t)(b >> 24);
+      if (aligned) *reinterpret_cast<uint32_t*>(p) = b;
+      else { p[0] = (uint8_t)b; p[1] = (uint8_t)(b >> 8); p[2] = (uint8_t)(b >> 16); p[3] = (uint8_t)(b >> 24); }
       p += 4;
     }
     return p;
@@ -100,7 +102,16 @@ __device__ __forceinline__ uint8_t* emit_list_body(uint8_t* p, const DevField& f
     uint32_t l = (uint32_t)(so[i + 1] - so[i]);
     *p++ = 0x0A; p = put_varint(p, l);
     const uint8_t* s = data + so[i];
-    for (uint32_t k = 0; k < l; ++k) p[k] = s[k];
+    uint32_t k = 0;
+    if ((reinterpret_cast<uintptr_t>(s) & 3u) == 0) {                           // word loads from the column, bytes (or words) into the record
+      const bool pal = (reinterpret_cast<uintptr_t>(p) & 3u) == 0;
+      for (; k + 4 <= l; k += 4) {
+        const uint32_t w = *reinterpret_cast<const uint32_t*>(s + k);
+        if (pal) *reinterpret_cast<uint32_t*>(p + k) = w;
+        else { p[k] = (uint8_t)w; p[k + 1] = (uint8_t)(w >> 8); p[k + 2] = (uint8_t)(w >> 16); p[k + 3] = (uint8_t)(w >> 24); }
+      }
+    }
+    for (; k < l; ++k) p[k] = s[k];
     p += l;
   }
   return p;

@@ -60,8 +60,19 @@ struct EncSizeArgs {
 };
 __global__ void __launch_bounds__(ENC_TILE_THREADS) encode_tile_size_kernel(EncSizeArgs A) {
   __shared__ uint32_t sacc[ENC_TILE_ROWS];
+  extern __shared__ __align__(16) uint8_t ssm[];              // fields | column pointers (enc_tile_meta_bytes(nf, 0)): no fields[f] -> cols[f] -> values chains
   const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const uint32_t nf = (uint32_t)A.sch.n_fields;
+  DevField* sfd = reinterpret_cast<DevField*>(ssm);
+  EncCol* scol = reinterpret_cast<EncCol*>(ssm + ((nf * (uint32_t)sizeof(DevField) + 15u) & ~15u));
+  {
+    const uint32_t* gf = reinterpret_cast<const uint32_t*>(A.sch.fields);
+    uint32_t* df = reinterpret_cast<uint32_t*>(sfd);
+    for (uint32_t i = threadIdx.x; i < nf * (uint32_t)(sizeof(DevField) / 4); i += ENC_TILE_THREADS) df[i] = gf[i];
+    const uint32_t* gc = reinterpret_cast<const uint32_t*>(A.cols);
+    uint32_t* dc = reinterpret_cast<uint32_t*>(scol);
+    for (uint32_t i = threadIdx.x; i < nf * (uint32_t)(sizeof(EncCol) / 4); i += ENC_TILE_THREADS) dc[i] = gc[i];
+  }
   const uint32_t row = blockIdx.x * ENC_TILE_ROWS + lane;
   const bool active = row < A.n_rows;
   if (threadIdx.x < ENC_TILE_ROWS) sacc[threadIdx.x] = 0;
@@ -70,8 +81,8 @@ __global__ void __launch_bounds__(ENC_TILE_THREADS) encode_tile_size_kernel(EncS
   bool null_err = false;
   if (active)
     for (uint32_t f = wid; f < nf; f += ENC_TILE_WARPS) {
-      const DevField& fd = A.sch.fields[f];
-      const uint32_t V = cell_value_size(fd, A.cols[f], row);
+      const DevField& fd = sfd[f];
+      const uint32_t V = cell_value_size(fd, scol[f], row);
       A.cell_size[(size_t)f * A.n_rows + row] = V;
       if (V == 0xffffffffu) { if (!fd.nullable) null_err = true; }      // NullPointerException (:29-31)
       else sum += entry_total(fd, V);
@@ -234,6 +245,7 @@ struct EncFusedArgs {
   unsigned long long* tile_state;      // [n_tiles] (flag << 62) | bytes; flag 1: this tile's bytes, 2: inclusive prefix; zeroed per call
   uint32_t* ticket;                    // [0], zeroed per call
   uint32_t* small;                     // [0] atomicMin first null-in-non-nullable row, [1] overflow, [2..3] total bytes, [4] atomicMax framed record size
+  uint32_t names_bytes;
 };
 
 #define ENC_LB_AGG (1ull << 62)
@@ -249,7 +261,11 @@ __global__ void __launch_bounds__(ENC_TILE_THREADS, 3) encode_fused_kernel(EncFu
   const uint32_t nf = (uint32_t)A.sch.n_fields;
   uint16_t* vsz = reinterpret_cast<uint16_t*>(sgrp + 32);
   uint16_t* eoff = vsz + nf * 32;
-  uint8_t* slots = esm + 4096 + 128 + 128 + ((nf * 32 * 2 * 2 + 15u) & ~15u);
+  uint8_t* meta = esm + 4096 + 128 + 128 + ((nf * 32 * 2 * 2 + 15u) & ~15u);
+  DevField* sfd = reinterpret_cast<DevField*>(meta);
+  EncCol* scol = reinterpret_cast<EncCol*>(meta + ((nf * (uint32_t)sizeof(DevField) + 15u) & ~15u));
+  uint8_t* snames = meta + ((nf * (uint32_t)sizeof(DevField) + 15u) & ~15u) + ((nf * (uint32_t)sizeof(EncCol) + 15u) & ~15u);
+  uint8_t* slots = meta + enc_tile_meta_bytes(nf, A.names_bytes);
   __shared__ uint32_t s_tile, s_bad, s_total, s_row[ENC_TILE_ROWS];
   __shared__ unsigned long long s_base;
   const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -264,6 +280,13 @@ __global__ void __launch_bounds__(ENC_TILE_THREADS, 3) encode_fused_kernel(EncFu
     const uint32_t* g = A.tabs->g5;
     for (uint32_t i = threadIdx.x; i < 1024; i += ENC_TILE_THREADS) g5[i] = g[i];
     if (threadIdx.x < 32) { scrc[threadIdx.x] = 0; sgrp[threadIdx.x] = 0; }
+    const uint32_t* gf = reinterpret_cast<const uint32_t*>(A.sch.fields);            // fields, column pointers, names: see encode_tile_kernel
+    uint32_t* df = reinterpret_cast<uint32_t*>(sfd);
+    for (uint32_t i = threadIdx.x; i < nf * (uint32_t)(sizeof(DevField) / 4); i += ENC_TILE_THREADS) df[i] = gf[i];
+    const uint32_t* gc = reinterpret_cast<const uint32_t*>(A.cols);
+    uint32_t* dc = reinterpret_cast<uint32_t*>(scol);
+    for (uint32_t i = threadIdx.x; i < nf * (uint32_t)(sizeof(EncCol) / 4); i += ENC_TILE_THREADS) dc[i] = gc[i];
+    for (uint32_t i = threadIdx.x; i < A.names_bytes; i += ENC_TILE_THREADS) snames[i] = A.sch.names[i];
   }
   __syncthreads();
   // ---- sizes: warp w takes fields w, w+W, ... of row `lane` ----
@@ -271,8 +294,8 @@ __global__ void __launch_bounds__(ENC_TILE_THREADS, 3) encode_fused_kernel(EncFu
     uint32_t sum = 0;
     bool null_err = false, big = false;
     for (uint32_t f = wid; f < nf; f += ENC_TILE_WARPS) {
-      const DevField& fd = A.sch.fields[f];
-      const uint32_t V = active ? cell_value_size(fd, A.cols[f], row) : 0xffffffffu;
+      const DevField& fd = sfd[f];
+      const uint32_t V = active ? cell_value_size(fd, scol[f], row) : 0xffffffffu;
       if (V == 0xffffffffu) { if (active && !fd.nullable) null_err = true; vsz[f * 32 + lane] = (uint16_t)0xffff; }
       else {
         if (V >= 0xffffu) big = true;
@@ -295,7 +318,7 @@ __global__ void __launch_bounds__(ENC_TILE_THREADS, 3) encode_fused_kernel(EncFu
     for (uint32_t f = 0; f < nf; ++f) {
       const uint32_t V = vsz[f * 32 + lane];
       eoff[f * 32 + lane] = (uint16_t)min(acc, 0xffffu);
-      if (V != 0xffffu) acc += entry_total(A.sch.fields[f], V);
+      if (V != 0xffffu) acc += entry_total(sfd[f], V);
     }
     uint32_t T;
     s_row[lane] = warp_excl_scan_u32(flen, T);
@@ -352,13 +375,13 @@ __global__ void __launch_bounds__(ENC_TILE_THREADS, 3) encode_fused_kernel(EncFu
     for (uint32_t f = wid; f < nf; f += ENC_TILE_WARPS) {
       const uint32_t V = vsz[f * 32 + lane];
       if (V == 0xffffu) continue;                                        // null: the feature is omitted (:29)
-      const DevField& fd = A.sch.fields[f];
-      const EncCol& c = A.cols[f];
+      const DevField& fd = sfd[f];
+      const EncCol& c = scol[f];
       uint8_t* p = rec + 12 + ghdr + eoff[f * 32 + lane];
       const uint32_t E = 1 + vsize32(fd.name_len) + fd.name_len + 1 + vsize32(V) + V;
       *p++ = 0x0A; p = put_varint(p, E);
       *p++ = 0x0A; p = put_varint(p, fd.name_len);
-      const uint8_t* nm = A.sch.names + fd.name_off;
+      const uint8_t* nm = snames + fd.name_off;
       for (uint32_t k = 0; k < fd.name_len; ++k) p[k] = nm[k];
       p += fd.name_len;
       *p++ = 0x12; p = put_varint(p, V);
@@ -405,9 +428,17 @@ __global__ void __launch_bounds__(ENC_TILE_THREADS, 3) encode_fused_kernel(EncFu
   // ---- copy-out ----
   uint8_t* dst0 = A.out + s_base;
   for (uint32_t r = wid; r < rows; r += ENC_TILE_WARPS) {
-    const uint8_t* s = slots + r * A.slot;
-    const uint32_t flen_r = 16 + *reinterpret_cast<const uint32_t*>(s);      // the framed length is in the record's own header
+    const uint32_t s0 = r * A.slot;                                           // 4-byte aligned
+    const uint32_t flen = 16 + T.w32(s0);                                     // the framed length is in the record's own header
     uint8_t* d = dst0 + s_row[r];
-    for (uint32_t i = lane; i < flen_r; i += 32) d[i] = s[i];
+    const uint32_t hm = min(flen, (0u - (uint32_t)reinterpret_cast<uintptr_t>(d)) & 3u);
+    if (lane < hm) d[lane] = (uint8_t)T.u8(s0 + lane);
+    const uint32_t words = (flen - hm) >> 2;
+    const uint32_t so = s0 + hm, sh = (so & 3u) * 8u, sa = so & ~3u;
+    uint32_t* dw = reinterpret_cast<uint32_t*>(d + hm);
+    if (sh == 0) for (uint32_t i = lane; i < words; i += 32) dw[i] = T.w32(sa + 4 * i);
+    else for (uint32_t i = lane; i < words; i += 32) dw[i] = __funnelshift_r(T.w32(sa + 4 * i), T.w32(sa + 4 * i + 4), sh);
+    const uint32_t tl = (flen - hm) & 3u;
+    if (lane < tl) d[hm + 4 * words + lane] = (uint8_t)T.u8(so + 4 * words + lane);
   }
 }
