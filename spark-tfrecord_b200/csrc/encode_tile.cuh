@@ -23,8 +23,12 @@
 #include "tile.cuh"
 
 #define ENC_TILE_ROWS 32
+#ifndef ENC_TILE_WARPS
 #define ENC_TILE_WARPS 8
+#endif
 #define ENC_TILE_THREADS (ENC_TILE_WARPS * 32)
+#define ENC_SIZE_WARPS 8          // the size pass: little shared memory, six CTAs per SM
+#define ENC_SIZE_THREADS (ENC_SIZE_WARPS * 32)
 
 struct EncTileArgs {
   DevSchema sch;
@@ -58,7 +62,7 @@ struct EncSizeArgs {
   uint32_t* cell_size;          // [n_fields][n_rows]
   uint32_t* small;              // [0] atomicMin first row with a null in a non-nullable column, [4] atomicMax framed record size
 };
-__global__ void __launch_bounds__(ENC_TILE_THREADS) encode_tile_size_kernel(EncSizeArgs A) {
+__global__ void __launch_bounds__(ENC_SIZE_THREADS, 6) encode_tile_size_kernel(EncSizeArgs A) {
   __shared__ uint32_t sacc[ENC_TILE_ROWS];
   extern __shared__ __align__(16) uint8_t ssm[];              // fields | column pointers (enc_tile_meta_bytes(nf, 0)): no fields[f] -> cols[f] -> values chains
   const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -68,10 +72,10 @@ __global__ void __launch_bounds__(ENC_TILE_THREADS) encode_tile_size_kernel(EncS
   {
     const uint32_t* gf = reinterpret_cast<const uint32_t*>(A.sch.fields);
     uint32_t* df = reinterpret_cast<uint32_t*>(sfd);
-    for (uint32_t i = threadIdx.x; i < nf * (uint32_t)(sizeof(DevField) / 4); i += ENC_TILE_THREADS) df[i] = gf[i];
+    for (uint32_t i = threadIdx.x; i < nf * (uint32_t)(sizeof(DevField) / 4); i += ENC_SIZE_THREADS) df[i] = gf[i];
     const uint32_t* gc = reinterpret_cast<const uint32_t*>(A.cols);
     uint32_t* dc = reinterpret_cast<uint32_t*>(scol);
-    for (uint32_t i = threadIdx.x; i < nf * (uint32_t)(sizeof(EncCol) / 4); i += ENC_TILE_THREADS) dc[i] = gc[i];
+    for (uint32_t i = threadIdx.x; i < nf * (uint32_t)(sizeof(EncCol) / 4); i += ENC_SIZE_THREADS) dc[i] = gc[i];
   }
   const uint32_t row = blockIdx.x * ENC_TILE_ROWS + lane;
   const bool active = row < A.n_rows;
@@ -80,7 +84,7 @@ __global__ void __launch_bounds__(ENC_TILE_THREADS) encode_tile_size_kernel(EncS
   uint32_t sum = 0;
   bool null_err = false;
   if (active)
-    for (uint32_t f = wid; f < nf; f += ENC_TILE_WARPS) {
+    for (uint32_t f = wid; f < nf; f += ENC_SIZE_WARPS) {
       const DevField& fd = sfd[f];
       const uint32_t V = cell_value_size(fd, scol[f], row);
       A.cell_size[(size_t)f * A.n_rows + row] = V;
