@@ -156,3 +156,38 @@ def test_random_schema_encode_is_byte_identical(native, oracle, seed):
             assert bytes(got) == bytes(want), f"seed {seed} (record type {rt}, {n} rows, call {it + 1}): encoded bytes differ"
     finally:
         enc.close()
+
+
+@pytest.mark.parametrize("seed", range(16))
+def test_random_damage_reports_the_oracles_error(native, oracle, seed):
+    """one flipped bit (anywhere: length, length CRC, payload, payload CRC) or a truncation at a random byte, in a batch submitted to
+    a decoder in its steady pipelined state: error code, error row, rows delivered, consumed bytes and the rows themselves are the
+    oracle's (the reference's iterator yields the rows before the bad record, then throws: M/TFRecordFileReader.scala:49-81)"""
+    import torch
+    rt = 1 if seed % 4 == 3 else 0
+    rng = np.random.default_rng(31000 + seed)
+    sch, gens = _schema(rng, seq=bool(rt))
+    clean = _batch(oracle, sch, gens, 2500, 100 + seed, rt)
+    dec = native.Decoder(sch, rt)
+    try:
+        b, _ = dec.decode(torch.from_numpy(clean.copy()).cuda()); b.release()
+        b = dec.submit(torch.from_numpy(clean.copy()).cuda()); assert b.info["error_code"] == 0; b.release()
+        for trial in range(6):
+            bad = clean.copy()
+            is_final = True
+            if trial == 5:
+                bad = bad[: int(rng.integers(1, len(bad)))]                       # truncated file
+                is_final = bool(trial % 2)
+            else:
+                pos = int(rng.integers(0, len(bad)))
+                bad[pos] ^= np.uint8(1 << int(rng.integers(0, 8)))
+            want = oracle.decode(bad, sch, rt, is_final=is_final)
+            bt = dec.submit(torch.from_numpy(bad.copy()).cuda(), is_final=is_final)
+            info = bt.info
+            for k in ("error_code", "error_row", "error_field", "n_rows", "consumed_bytes"):
+                assert info[k] == want.info[k], (seed, trial, k, info, want.info)
+            assert_columns_equal(bt.to_host(), want.columns, sch.names, f"damage seed {seed} trial {trial}")
+            bt.release()
+            b = dec.submit(torch.from_numpy(clean.copy()).cuda()); assert b.info["error_code"] == 0 and b.n_rows == 2500; b.release()
+    finally:
+        dec.close()
