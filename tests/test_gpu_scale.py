@@ -653,3 +653,48 @@ def test_consumed_is_known_before_the_rows(native, oracle):
         b.release()
     finally:
         dec.close()
+
+
+def test_bytearray_encode_single_pass(native, oracle):
+    """recordType=ByteArray rows -> framed records through encode_bytes_kernel: byte-identical to the oracle writer for host
+    columns, for device columns whose values pointer is misaligned and whose offsets do not start at 0 (a sliced Arrow array),
+    and through the general kernels when a row is too large for a tile (serializeByteArray M/TFRecordSerializer.scala:16-18)"""
+    import torch
+    from spark_tfrecord_b200._cabi import tfr_column
+    rng = np.random.default_rng(77)
+    sch = byte_array_schema()
+    for n, hi in ((1, 5), (33, 40), (50000, 2000), (20000, 300)):
+        sizes = rng.integers(0, hi, n)
+        sizes[:: 53] = 0
+        rows = [(rng.integers(0, 256, int(s), dtype=np.uint8).tobytes(),) for s in sizes]
+        cols = A.columns_from_rows(sch, rows)
+        want, rc, _ = oracle.encode(cols, sch, TFR_RT_BYTE_ARRAY)
+        assert rc == 0
+        enc = native.Encoder(sch, TFR_RT_BYTE_ARRAY, 0)
+        try:
+            for it in range(2):
+                assert bytes(enc.encode(cols)) == bytes(want), f"{n} ByteArray rows, call {it + 1}"
+            # the same rows as a slice of a larger device-resident Arrow array: 7 junk bytes in front, values at an odd address
+            c = cols[0]
+            junk = rng.integers(0, 256, 7, dtype=np.uint8)
+            vals = torch.from_numpy(np.concatenate([np.zeros(5, np.uint8), junk, c.values.view(np.uint8)])).cuda()
+            offs = torch.from_numpy((c.offsets[0].astype(np.int64) + 7).astype(np.int32)).cuda()
+            valid = torch.from_numpy(c.validity).cuda()
+            t = tfr_column()
+            hc = c.to_ctypes()
+            for f, _ in tfr_column._fields_:
+                setattr(t, f, getattr(hc, f))
+            t.validity = valid.data_ptr(); t.offsets[0] = offs.data_ptr(); t.values = vals.data_ptr() + 5
+            enc.encode_columns([t], True)
+            assert bytes(enc.result_host()) == bytes(want), f"{n} ByteArray rows, sliced device column"
+        finally:
+            enc.close()
+    # one row larger than any tile: the general kernels take the batch
+    rows = [(rng.integers(0, 256, int(s), dtype=np.uint8).tobytes(),) for s in list(rng.integers(0, 500, 100)) + [300000] + list(rng.integers(0, 500, 100))]
+    cols = A.columns_from_rows(sch, rows)
+    want, rc, _ = oracle.encode(cols, sch, TFR_RT_BYTE_ARRAY)
+    enc = native.Encoder(sch, TFR_RT_BYTE_ARRAY, 0)
+    try:
+        assert bytes(enc.encode(cols)) == bytes(want)
+    finally:
+        enc.close()
